@@ -1,0 +1,41 @@
+/* TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+ * Plain-C restatement of the RcppSMC 0.2.9 SMC hot path (see smc_oracle.c for the file:line map).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (rcppsmc_b200/) never does. */
+#ifndef SMC_ORACLE_H
+#define SMC_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SMCO_MULTINOMIAL = 0, SMCO_RESIDUAL = 1, SMCO_STRATIFIED = 2, SMCO_SYSTEMATIC = 3 };
+
+double smco_lse(const double* logw, long n);
+double smco_ess(const double* logw, long n);
+void smco_normalised_weights(const double* logw, long n, double* w);
+void smco_quantise_weights(const double* w, long n, double* wq);
+void smco_cumsum(const double* w, long n, double* W);
+
+long smco_counts_systematic(const double* w, long n, double U, int* count);
+long smco_counts_stratified(const double* w, long n, const double* U, int* count);
+long smco_counts_multinomial_iid(const double* w, long n, long ndraws, const double* U, int* count);
+long smco_residual_floor(const double* w, long n, int* floor_count, double* resid_w);
+void smco_counts_to_indices(int* count, long n, unsigned* idx);
+int smco_resample_from_weights(int mode, const double* w, long n, const double* U, long nU,
+                               const int* counts_in, unsigned* idx, int* count_out);
+int smco_resample(int mode, const double* logw, long n, const double* U, long nU,
+                  const int* counts_in, unsigned* idx, int* count_out);
+double smco_integrate(const double* logw, const double* f, long n);
+
+void smco_sim_nonlin(long T, const double* z_state, const double* z_obs, double var_init,
+                     double var_evol, double var_obs, double cos_offset, double* x, double* y);
+int smco_pfnonlinbs(const double* y, long T, long N, int mode, double threshold, const double* z,
+                    const double* U, unsigned long long seed, double* mean, double* sd,
+                    double* lognc, double* ess, int* resampled, unsigned* idx_trace);
+double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
+                            unsigned long long seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
