@@ -1,0 +1,100 @@
+/* smcb200 -- C ABI of the B200-native SMC engine (libsmcb200.so).
+ *
+ * This is the drop-in boundary for the SMC hot path of RcppSMC 0.2.9: the Rcpp glue
+ * (reference src/RcppExports.cpp:15-139) keeps its eight .Call routines and forwards the numeric work to
+ * these entry points instead of instantiating smc::sampler<Space,Params> on the CPU (INTEGRATION.md shows
+ * the stub).  Plain pointers and sizes only; all buffers named `host` are caller-owned host memory.
+ * No C++ exception crosses this boundary: every function returns a status and smcb200_last_error() gives
+ * the message (the analogue of the reference's smc::exception / Rcpp::stop, smc-exception.h:52-75).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with SMCB200_ERR_CUDA.
+ * One handle = one caller thread at a time (the reference is not re-entrant at all: file-scope model
+ * globals, inst/include/pfnonlinbs.h:50).
+ */
+#ifndef SMCB200_H
+#define SMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB200_OK 0
+#define SMCB200_ERR_INVALID 1 /* bad argument (message in smcb200_last_error) */
+#define SMCB200_ERR_CUDA 2    /* CUDA runtime failure or no device */
+#define SMCB200_ERR_STATE 3   /* call order violation (e.g. read before run) */
+
+/* ResampleType::Enum, reference inst/include/sampler.h:45-51 (same numeric values). */
+#define SMCB200_MULTINOMIAL 0
+#define SMCB200_RESIDUAL 1
+#define SMCB200_STRATIFIED 2
+#define SMCB200_SYSTEMATIC 3
+
+const char* smcb200_last_error(void);
+int smcb200_version(void);
+/* Number of visible CUDA devices (0 when none / no driver); never fails. */
+int smcb200_device_count(void);
+
+/* ---- unit level ------------------------------------------------------------------------------------- */
+
+/* Philox4x32-10 block function (known-answer surface for the RNG that replaces R's; host computation). */
+int smcb200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* n standard normals exactly as the engine draws them for (seed, stream, step): particle i gets out[i].
+ * Runs on the device. */
+int smcb200_philox_normals(uint64_t seed, uint32_t stream, uint32_t step, long n, double* out_host);
+
+/* Replaces smc::stableLogSumWeights (population.h:46-50) and sampler::GetESS (sampler.h:413-417).
+ * out3 = { log sum exp(logw), ESS = (sum w)^2 / sum w^2, max(logw) }. */
+int smcb200_lse(const double* logw_host, long n, double* out3_host);
+
+/* Replaces sampler::Resample's count + index stages (sampler.h:786-857) on NORMALISED weights.
+ *   weights      n normalised weights (quantised internally to the 2^-52 grid; weights already on the grid
+ *                give ancestor indices bit-identical to the reference for SYSTEMATIC / STRATIFIED)
+ *   uniforms     U in [0,1): SYSTEMATIC 1 value; STRATIFIED n+1 values (reference draw order, :810-819);
+ *                MULTINOMIAL n values, RESIDUAL n values (native iid inverse-CDF definition)
+ *   counts_in    optional: children counts to map directly (replaces rmultinom's output, :790/:801);
+ *                when given, weights / uniforms may be NULL
+ *   idx_out      n ancestor indices = uRSIndices (:845-857)
+ *   counts_out   optional: n children counts */
+int smcb200_resample(int mode, const double* weights_host, long n, const double* uniforms_host, long n_uniforms,
+                     const int* counts_in_host, unsigned int* idx_out_host, int* counts_out_host);
+
+/* ---- model level: pfNonlinBS (reference src/pfnonlinbs.cpp:52-79, R/pfNonlinBS.R) ------------------- */
+
+/* One-shot filter, the call the Rcpp wrapper makes.  `data` = y[0..T), `particles` = N.
+ * Reference behaviour is resample_mode = SMCB200_MULTINOMIAL, threshold = 1.01*N (src/pfnonlinbs.cpp:62).
+ *   seed      Philox key (the reference uses R's global RNG instead)
+ *   noise     optional N*T injected standard normals in the reference's consumption order
+ *             (N for Initialise, then N per Iterate), else NULL -> Philox
+ *   uniforms  optional injected resampling uniforms, indexed by step: SYSTEMATIC uniforms[t];
+ *             STRATIFIED uniforms[t*(N+1) + j]; else NULL -> Philox
+ * Outputs (length T each; any may be NULL): mean, sd as returned by pfNonlinBS_impl (:77-78); lognc =
+ * GetLogNCPath() after each step; ess = the ESS each step's resampling decision saw; resampled flags. */
+int smcb200_pfNonlinBS(const double* data_host, long T, long particles, int resample_mode, double threshold,
+                       uint64_t seed, const double* noise_host, const double* uniforms_host, double* mean_host,
+                       double* sd_host, double* lognc_host, double* ess_host, int* resampled_host);
+
+/* Handle-based variant: buffers live across runs so a benchmark can separate allocation / transfers from the
+ * filter itself.  `stream` is a cudaStream_t (NULL = default stream); all work of the handle is enqueued there. */
+typedef struct smcb200_pf smcb200_pf;
+int smcb200_pfNonlinBS_create(long particles, long tcap, uint64_t seed, void* stream, smcb200_pf** out);
+int smcb200_pfNonlinBS_set_data(smcb200_pf* h, const double* data_host, long T);
+int smcb200_pfNonlinBS_set_noise(smcb200_pf* h, const double* noise_host, const double* uniforms_host, long n_uniforms);
+/* Enqueues Initialise + (T-1) Iterate + the final moment pass; asynchronous. */
+int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold);
+int smcb200_pfNonlinBS_sync(smcb200_pf* h);
+/* Device time of the last run in milliseconds (CUDA events on the handle's stream). */
+int smcb200_pfNonlinBS_elapsed_ms(smcb200_pf* h, float* ms);
+int smcb200_pfNonlinBS_read(smcb200_pf* h, double* mean_host, double* sd_host, double* lognc_host, double* ess_host,
+                            int* resampled_host);
+/* Ancestor indices (uRSIndices) of the last step's resampling; identity if it did not resample. */
+int smcb200_pfNonlinBS_read_ancestors(smcb200_pf* h, unsigned int* idx_host);
+/* Kernel launches issued by the last run (for benchmark bookkeeping). */
+long smcb200_pfNonlinBS_launches(smcb200_pf* h);
+int smcb200_pfNonlinBS_destroy(smcb200_pf* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB200_H */

@@ -1,0 +1,195 @@
+"""ctypes binding of include/smcb200.h.  Fails loudly when the CUDA extension is absent."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+MULTINOMIAL, RESIDUAL, STRATIFIED, SYSTEMATIC = 0, 1, 2, 3  # ResampleType::Enum (reference sampler.h:45-51)
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_uint_p = ctypes.POINTER(ctypes.c_uint)
+_c_u32_p = ctypes.POINTER(ctypes.c_uint32)
+
+
+class SmcError(RuntimeError):
+    """Raised for any non-zero status of the C ABI (the analogue of smc::exception / Rcpp::stop)."""
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    """Loads libsmcb200.so (never builds implicitly on import; __graft_entry__.build() or _build.build() does)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SmcError(
+            f"{path} is missing: the CUDA extension is not built (run `python -m rcppsmc_b200._build`); "
+            "rcppsmc_b200 has no CPU fallback")
+    L = ctypes.CDLL(path)
+    L.smcb200_last_error.restype = ctypes.c_char_p
+    L.smcb200_version.restype = ctypes.c_int
+    L.smcb200_device_count.restype = ctypes.c_int
+    L.smcb200_philox4x32.argtypes = [_c_u32_p, _c_u32_p, _c_u32_p]
+    L.smcb200_philox_normals.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_long, _c_double_p]
+    L.smcb200_lse.argtypes = [_c_double_p, ctypes.c_long, _c_double_p]
+    L.smcb200_resample.argtypes = [ctypes.c_int, _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, _c_int_p,
+                                   _c_uint_p, _c_int_p]
+    L.smcb200_pfNonlinBS.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double,
+                                     ctypes.c_uint64, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
+                                     _c_double_p, _c_double_p, _c_int_p]
+    L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
+                                            ctypes.POINTER(ctypes.c_void_p)]
+    L.smcb200_pfNonlinBS_set_data.argtypes = [ctypes.c_void_p, _c_double_p, ctypes.c_long]
+    L.smcb200_pfNonlinBS_set_noise.argtypes = [ctypes.c_void_p, _c_double_p, _c_double_p, ctypes.c_long]
+    L.smcb200_pfNonlinBS_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    L.smcb200_pfNonlinBS_sync.argtypes = [ctypes.c_void_p]
+    L.smcb200_pfNonlinBS_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    L.smcb200_pfNonlinBS_read.argtypes = [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p]
+    L.smcb200_pfNonlinBS_read_ancestors.argtypes = [ctypes.c_void_p, _c_uint_p]
+    L.smcb200_pfNonlinBS_launches.argtypes = [ctypes.c_void_p]
+    L.smcb200_pfNonlinBS_launches.restype = ctypes.c_long
+    L.smcb200_pfNonlinBS_destroy.argtypes = [ctypes.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise SmcError(f"smcb200 status {rc}: {lib().smcb200_last_error().decode()}")
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_c_double_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    return lib().smcb200_device_count()
+
+
+def philox4x32(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    _check(lib().smcb200_philox4x32(c.ctypes.data_as(_c_u32_p), k.ctypes.data_as(_c_u32_p), out.ctypes.data_as(_c_u32_p)))
+    return out
+
+
+def philox_normals(seed, stream, step, n):
+    out = np.empty(n, dtype=np.float64)
+    _check(lib().smcb200_philox_normals(seed, stream, step, n, _dp(out)))
+    return out
+
+
+def log_sum_exp(logw):
+    """(log sum exp(logw), ESS, max) -- smc::stableLogSumWeights (population.h:46-50) + GetESS (sampler.h:413-417)."""
+    lw = _f64(logw)
+    out = np.zeros(3)
+    _check(lib().smcb200_lse(_dp(lw), lw.size, _dp(out)))
+    return float(out[0]), float(out[1]), float(out[2])
+
+
+def resample(mode, weights=None, uniforms=None, counts=None, return_counts=False):
+    """Ancestor indices (uRSIndices) for normalised ``weights`` -- sampler::Resample (sampler.h:786-857)."""
+    w = _f64(weights)
+    u = _f64(np.atleast_1d(uniforms)) if uniforms is not None else None
+    c = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+    n = w.size if w is not None else c.size
+    idx = np.empty(n, dtype=np.uint32)
+    cout = np.empty(n, dtype=np.int32) if return_counts else None
+    _check(lib().smcb200_resample(mode, _dp(w), n, _dp(u), 0 if u is None else u.size,
+                                  None if c is None else c.ctypes.data_as(_c_int_p), idx.ctypes.data_as(_c_uint_p),
+                                  None if cout is None else cout.ctypes.data_as(_c_int_p)))
+    return (idx, cout) if return_counts else idx
+
+
+def pfNonlinBS(data, particles, resample_mode=MULTINOMIAL, threshold=None, seed=1, noise=None, uniforms=None,
+               full=False):
+    """Mirror of ``pfNonlinBS_impl(data, part)`` (reference src/pfnonlinbs.cpp:52-79): returns dict(mean, sd).
+
+    The two reference arguments come first; the trailing ones are the extensions listed in include/smcb200.h
+    (the reference hard-codes MULTINOMIAL with threshold 1.01 N).  ``full=True`` adds logNC / ESS / resampled traces.
+    """
+    y = _f64(data)
+    T = y.size
+    thr = 1.01 * particles if threshold is None else threshold
+    mean, sd = np.empty(T), np.empty(T)
+    lognc, ess, res = np.empty(T), np.empty(T), np.empty(T, dtype=np.int32)
+    z = _f64(noise)
+    u = _f64(uniforms)
+    _check(lib().smcb200_pfNonlinBS(_dp(y), T, particles, resample_mode, thr, seed, _dp(z), _dp(u), _dp(mean), _dp(sd),
+                                    _dp(lognc), _dp(ess), res.ctypes.data_as(_c_int_p)))
+    out = {"mean": mean, "sd": sd}
+    if full:
+        out.update(logNC=lognc, ESS=ess, resampled=res)
+    return out
+
+
+class PfNonlinBS:
+    """Handle-based filter: device buffers persist across runs (benchmarking, repeated filtering)."""
+
+    def __init__(self, particles, tcap, seed=1, stream=None):
+        self._h = ctypes.c_void_p()
+        self.particles, self.tcap = particles, tcap
+        _check(lib().smcb200_pfNonlinBS_create(particles, tcap, seed, stream, ctypes.byref(self._h)))
+        self.T = 0
+
+    def set_data(self, data):
+        y = _f64(data)
+        self.T = y.size
+        _check(lib().smcb200_pfNonlinBS_set_data(self._h, _dp(y), y.size))
+
+    def set_noise(self, noise=None, uniforms=None):
+        z, u = _f64(noise), _f64(uniforms)
+        _check(lib().smcb200_pfNonlinBS_set_noise(self._h, _dp(z), _dp(u), 0 if u is None else u.size))
+
+    def run(self, resample_mode=SYSTEMATIC, threshold=None):
+        thr = 1.01 * self.particles if threshold is None else threshold
+        _check(lib().smcb200_pfNonlinBS_run(self._h, resample_mode, thr))
+
+    def sync(self):
+        _check(lib().smcb200_pfNonlinBS_sync(self._h))
+
+    def elapsed_ms(self):
+        ms = ctypes.c_float()
+        _check(lib().smcb200_pfNonlinBS_elapsed_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def read(self):
+        T = self.T
+        mean, sd, lognc, ess = np.empty(T), np.empty(T), np.empty(T), np.empty(T)
+        res = np.empty(T, dtype=np.int32)
+        _check(lib().smcb200_pfNonlinBS_read(self._h, _dp(mean), _dp(sd), _dp(lognc), _dp(ess), res.ctypes.data_as(_c_int_p)))
+        return {"mean": mean, "sd": sd, "logNC": lognc, "ESS": ess, "resampled": res}
+
+    def read_ancestors(self):
+        idx = np.empty(self.particles, dtype=np.uint32)
+        _check(lib().smcb200_pfNonlinBS_read_ancestors(self._h, idx.ctypes.data_as(_c_uint_p)))
+        return idx
+
+    def launches(self):
+        return lib().smcb200_pfNonlinBS_launches(self._h)
+
+    def close(self):
+        if self._h:
+            lib().smcb200_pfNonlinBS_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,96 @@
+// Shared device helpers: warp/block reductions, the log-sum-exp monoid, control block, error handling.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+namespace smcb {
+
+#define SMCB_FULL 0xffffffffu
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+        throw CudaError(buf);
+    }
+}
+#define SMCB_CUDA(x) ::smcb::cuda_check((x), #x, __FILE__, __LINE__)
+
+// Resampling modes / history modes: numeric values are the reference's (inst/include/sampler.h:45-68).
+enum ResampleMode : int { MULTINOMIAL = 0, RESIDUAL = 1, STRATIFIED = 2, SYSTEMATIC = 3 };
+enum HistoryMode : int { HISTORY_NONE = 0, HISTORY_RAM = 1, HISTORY_AL = 2 };
+
+__device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(SMCB_FULL, v, off); }
+__device__ __forceinline__ double shfl_xor_d(double v, int off) { return __shfl_xor_sync(SMCB_FULL, v, off); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_xor_d(v, o));
+    return v;
+}
+
+// (m, s, q, g[]) with s = sum exp(lw - m), q = sum exp(2(lw - m)), g_j = sum exp(lw - m) h_j: an associative,
+// commutative monoid under max-rescaled addition.  It carries everything the reference
+// derives from stableLogSumWeights (population.h:46-50): logNC increment = m + log s (sampler.h:498,710),
+// ESS = s^2 / q (sampler.h:413-417), weighted means g/s (sampler.h:559-571).
+template <int G>
+struct LseAcc {
+    double m, s, q;
+    double g[G > 0 ? G : 1];
+    __device__ __forceinline__ void clear() {
+        m = -INFINITY; s = 0.0; q = 0.0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) g[j] = 0.0;
+    }
+    // add one element: exactly one exp
+    __device__ __forceinline__ void add(double lw, const double* h) {
+        if (lw == -INFINITY && m == -INFINITY) return;  // weightless particle, nothing to rescale
+        double d = lw - m;
+        double e = exp(-fabs(d));
+        if (d <= 0.0) {
+            s += e; q = fma(e, e, q);
+#pragma unroll
+            for (int j = 0; j < G; ++j) g[j] = fma(e, h[j], g[j]);
+        } else {
+            s = fma(s, e, 1.0); q = fma(q, e * e, 1.0);
+#pragma unroll
+            for (int j = 0; j < G; ++j) g[j] = fma(g[j], e, h[j]);
+            m = lw;
+        }
+    }
+    __device__ __forceinline__ void merge(const LseAcc& o) {
+        if (o.m == -INFINITY) return;
+        if (m == -INFINITY) { *this = o; return; }
+        double M = fmax(m, o.m);
+        double ea = exp(m - M), eb = exp(o.m - M);
+        s = s * ea + o.s * eb;
+        q = q * (ea * ea) + o.q * (eb * eb);
+#pragma unroll
+        for (int j = 0; j < G; ++j) g[j] = g[j] * ea + o.g[j] * eb;
+        m = M;
+    }
+    __device__ __forceinline__ LseAcc shfl_xor(int off) const {
+        LseAcc r;
+        r.m = shfl_xor_d(m, off); r.s = shfl_xor_d(s, off); r.q = shfl_xor_d(q, off);
+#pragma unroll
+        for (int j = 0; j < G; ++j) r.g[j] = shfl_xor_d(g[j], off);
+        return r;
+    }
+    __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { LseAcc t = shfl_xor(o); merge(t); }
+    }
+};
+
+}  // namespace smcb

@@ -1,0 +1,445 @@
+// Device SMC engine: the reference's smc::sampler loop (inst/include/sampler.h:481-550 Initialise,
+// :701-764 IterateEss) re-designed as two kernels per time step that never return to the host:
+//
+//   k_step   gather(ancestor) + pfMove/pfInitialise functor + log-weight + online (m, s, q, g) partials
+//            + fused weighted moments of the PREVIOUS population; the last block to finish merges the
+//            partials and writes the step scalars (logNC increment, path, ESS, resample decision, the
+//            resampling uniform) into the device control block  -> moveset.h:133-168, sampler.h:495-511,
+//            :707-723, :559-571
+//   k_resample_scan (resample.cuh)   weights -> ancestor map, skipped on device when ESS >= threshold
+//
+// Population layout: structure-of-arrays, D double arrays of length N, double-buffered (the gather is
+// out-of-place), one log-weight array; the reference's AoS std::vector<Space> + arma::vec
+// (population.h:53-112) is never materialised on the device.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "resample.cuh"
+
+namespace smcb {
+
+constexpr int MAX_OBS = 8;
+constexpr int MAX_SHIFT = 4;
+constexpr int STEP_THREADS = 256;
+
+// Device control block: every per-step scalar of the reference sampler lives here so that a whole filter
+// runs without host round trips.  Field meanings follow sampler.h:88-128.
+struct Ctrl {
+    long long T;            // evolution time (sampler::T)
+    double lse;             // dlogNCIt: normaliser of the log-weights currently stored
+    double lognc_path;      // dlogNCPath
+    double ess;             // ESS measured before the resampling decision of the current step
+    double u_res;           // base uniform in [0,1) for the current step's resampling
+    double thr;             // dResampleThreshold (absolute)
+    double log_n;           // log(N)
+    double shift[MAX_SHIFT];  // centring constants for the fused moment pass (pre-resample weighted means)
+    int resampled;          // nResampled: ancestor map is pending for the next gather
+    int parity;             // which state buffer holds the current population
+    unsigned int done;      // last-block-done counter
+    unsigned int ticket;    // scan tile ticket
+    int n_accepted;
+    int pad;
+};
+
+struct Traces {             // device arrays of length Tcap
+    double* lognc;          // dlogNCPath after each step
+    double* ess;            // pre-resample ESS of each step
+    int* resampled;
+    double* obs;            // [Tcap][NOBS] fused observables
+};
+
+template <class Model>
+struct StepArgs {
+    double* xa[Model::D];
+    double* xb[Model::D];
+    double* lw;
+    long long n;
+    AncestorMap am;
+    Ctrl* ctrl;
+    Traces tr;
+    double* partial;            // [(4 + NSHIFT + NOBS)][gridDim.x]
+    unsigned long long* status; // scan status arrays to clear for the next resampling pass (3 * ntiles)
+    long long nstatus;
+    typename Model::Params params;
+    unsigned long long seed;
+    const double* znoise;       // injected standard normals in the reference's consumption order, or null
+    const double* ures;         // injected resampling base uniforms, one per step, or null
+    long long tcap;
+};
+
+enum { PHASE_INIT = 0, PHASE_MOVE = 1, PHASE_OBSERVE = 2 };
+
+template <class Model, int PHASE, bool INJECT>
+__global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
+    constexpr int D = Model::D, G = Model::NSHIFT, NOBS = Model::NOBS;
+    constexpr int NZ = PHASE == PHASE_INIT ? Model::NZ_INIT : Model::NZ_MOVE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n = a.n;
+
+    // ---- snapshot of the control block (stable until the last block's finalize)
+    const long long T = a.ctrl->T;
+    const int resampled = PHASE == PHASE_INIT ? 0 : a.ctrl->resampled;
+    const double lse_prev = a.ctrl->lse;
+    const double log_n = a.ctrl->log_n;
+    const int parity = a.ctrl->parity;
+    double shift[G > 0 ? G : 1];
+#pragma unroll
+    for (int j = 0; j < G; ++j) shift[j] = a.ctrl->shift[j];
+    const long long tcur = PHASE == PHASE_INIT ? 0 : T + 1;  // lTime handed to the model (sampler.h:733,776)
+
+    double* const* src = parity ? a.xb : a.xa;
+    double* const* dst = parity ? a.xa : a.xb;
+
+    // ---- clear the look-back status words for the resampling pass that follows this kernel
+    for (long long i = (long long)blockIdx.x * STEP_THREADS + tid; i < a.nstatus; i += (long long)gridDim.x * STEP_THREADS)
+        a.status[i] = 0ull;
+
+    LseAcc<G> acc;
+    acc.clear();
+    double obs0 = 0.0, obs[NOBS > 0 ? NOBS : 1];
+#pragma unroll
+    for (int j = 0; j < NOBS; ++j) obs[j] = 0.0;
+
+    const long long npairs = (n + 1) >> 1;
+    for (long long p = (long long)blockIdx.x * STEP_THREADS + tid; p < npairs; p += (long long)gridDim.x * STEP_THREADS) {
+        const long long s0 = 2 * p;
+        const bool has1 = s0 + 1 < n;
+        double x[2][D], lwv[2];
+        // ---- gather the previous population (sampler.h:860-864 replication, fused)
+        if (PHASE != PHASE_INIT) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                long long s = s0 + h;
+                if (h == 1 && !has1) break;
+                long long anc = s;
+                double lwp;
+                if (resampled) { anc = decode_ancestor(a.am, s); lwp = -log_n; }
+                else lwp = a.lw[s] - lse_prev;
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[h][d] = src[d][anc];
+                lwv[h] = lwp;
+                if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
+                    double f[NOBS > 0 ? NOBS : 1];
+                    Model::observe(x[h], shift, f);
+                    double w = resampled ? 1.0 : exp(lwp);
+                    obs0 += w;
+#pragma unroll
+                    for (int j = 0; j < NOBS; ++j) obs[j] = fma(w, f[j], obs[j]);
+                }
+            }
+        }
+        if (PHASE != PHASE_OBSERVE) {
+            // ---- standard normals: one Philox + Box-Muller per pair and draw slot, or the injected stream
+            double z[2][NZ > 0 ? NZ : 1];
+            if (INJECT) {
+                long long off = PHASE == PHASE_INIT ? 0 : n * Model::NZ_INIT + (tcur - 1) * n * Model::NZ_MOVE;
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) {
+                    z[0][k] = a.znoise[off + s0 * NZ + k];
+                    z[1][k] = has1 ? a.znoise[off + (s0 + 1) * NZ + k] : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NZ; ++k)
+                    philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur, (uint64_t)p, k, z[0][k], z[1][k]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !has1) break;
+                long long s = s0 + h;
+                double lw;
+                if (PHASE == PHASE_INIT) {
+                    Model::init(x[h], lw, a.params, z[h]);   // moveset.h:133-138
+                    lw = lw - log_n;                          // sampler.h:495
+                } else {
+                    lw = lwv[h];
+                    Model::move(tcur, x[h], lw, a.params, z[h]);  // moveset.h:162-168
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) dst[d][s] = x[h][d];
+                a.lw[s] = lw;
+                double hs[G > 0 ? G : 1];
+                Model::shift_stat(x[h], hs);
+                acc.add(lw, hs);
+            }
+        }
+    }
+
+    // ---- block reduction
+    constexpr int NF = 4 + G + NOBS;  // m, s, q, obs0, g[G], obs[NOBS]
+    __shared__ double s_red[STEP_THREADS / 32][NF];
+    __shared__ bool s_last;
+    acc.warp_reduce();
+    obs0 = warp_sum(obs0);
+#pragma unroll
+    for (int j = 0; j < NOBS; ++j) obs[j] = warp_sum(obs[j]);
+    if (lane == 0) {
+        s_red[warp][0] = acc.m; s_red[warp][1] = acc.s; s_red[warp][2] = acc.q; s_red[warp][3] = obs0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) s_red[warp][4 + j] = acc.g[j];
+#pragma unroll
+        for (int j = 0; j < NOBS; ++j) s_red[warp][4 + G + j] = obs[j];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        LseAcc<G> b; b.clear();
+        double o0 = 0.0, o[NOBS > 0 ? NOBS : 1];
+#pragma unroll
+        for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
+        for (int w = 0; w < STEP_THREADS / 32; ++w) {
+            LseAcc<G> t;
+            t.m = s_red[w][0]; t.s = s_red[w][1]; t.q = s_red[w][2];
+#pragma unroll
+            for (int j = 0; j < G; ++j) t.g[j] = s_red[w][4 + j];
+            b.merge(t);
+            o0 += s_red[w][3];
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) o[j] += s_red[w][4 + G + j];
+        }
+        const int nb = gridDim.x;
+        double* P = a.partial;
+        P[0 * nb + blockIdx.x] = b.m; P[1 * nb + blockIdx.x] = b.s; P[2 * nb + blockIdx.x] = b.q; P[3 * nb + blockIdx.x] = o0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) P[(4 + j) * nb + blockIdx.x] = b.g[j];
+#pragma unroll
+        for (int j = 0; j < NOBS; ++j) P[(4 + G + j) * nb + blockIdx.x] = o[j];
+        __threadfence();
+        unsigned prev = atomicAdd(&a.ctrl->done, 1u);
+        s_last = (prev == (unsigned)nb - 1u);
+    }
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+
+    // ---- last block, warp 0: merge the per-block partials in a fixed order and close the step
+    __threadfence();
+    {
+        const int nb = gridDim.x;
+        const volatile double* P = a.partial;
+        LseAcc<G> b; b.clear();
+        double o0 = 0.0, o[NOBS > 0 ? NOBS : 1];
+#pragma unroll
+        for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
+        for (int k = lane; k < nb; k += 32) {
+            LseAcc<G> t;
+            t.m = P[0 * nb + k]; t.s = P[1 * nb + k]; t.q = P[2 * nb + k];
+#pragma unroll
+            for (int j = 0; j < G; ++j) t.g[j] = P[(4 + j) * nb + k];
+            b.merge(t);
+            o0 += P[3 * nb + k];
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) o[j] += P[(4 + G + j) * nb + k];
+        }
+        b.warp_reduce();
+        o0 = warp_sum(o0);
+#pragma unroll
+        for (int j = 0; j < NOBS; ++j) o[j] = warp_sum(o[j]);
+        if (lane == 0) {
+            Ctrl* c = a.ctrl;
+            if (PHASE != PHASE_INIT && NOBS > 0 && T < a.tcap) {
+                double v[NOBS > 0 ? NOBS : 1], out[NOBS > 0 ? NOBS : 1];
+#pragma unroll
+                for (int j = 0; j < NOBS; ++j) v[j] = o[j] / o0;
+                Model::finish_obs(v, shift, out);
+#pragma unroll
+                for (int j = 0; j < NOBS; ++j) a.tr.obs[T * NOBS + j] = out[j];
+            }
+            if (PHASE != PHASE_OBSERVE) {
+                double lse = b.m + log(b.s);                 // stableLogSumWeights, population.h:46-50
+                double path = (PHASE == PHASE_INIT ? 0.0 : c->lognc_path) + lse;  // sampler.h:498-499, :710-711
+                double ess = (b.s * b.s) / b.q;              // sampler.h:413-417 on the normalised weights
+                int res = ess < c->thr ? 1 : 0;              // sampler.h:507, :719
+                c->lse = lse; c->lognc_path = path; c->ess = ess; c->resampled = res;
+                c->T = tcur; c->parity = parity ^ 1;
+#pragma unroll
+                for (int j = 0; j < G; ++j) c->shift[j] = b.g[j] / b.s;
+                double U;
+                if (a.ures) U = a.ures[tcur];
+                else U = u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
+                c->u_res = U;
+                if (tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
+            }
+            c->ticket = 0u;
+            c->done = 0u;
+        }
+    }
+}
+
+// Number of persistent blocks for a kernel: all SMs x resident blocks, capped by the work available.
+template <class K>
+inline int persistent_grid(K kernel, int threads, long long work_items, int items_per_block) {
+    int dev = 0, sms = 0, per_sm = 0;
+    SMCB_CUDA(cudaGetDevice(&dev));
+    SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long need = (work_items + items_per_block - 1) / items_per_block;
+    long long g = (long long)sms * per_sm;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// Host-side owner of one particle system.  Method names follow the reference sampler (sampler.h:133-237).
+template <class Model>
+class Sampler {
+public:
+    static constexpr int D = Model::D, NOBS = Model::NOBS, G = Model::NSHIFT;
+
+    Sampler(long long n, long long tcap, unsigned long long seed, cudaStream_t stream = 0)
+        : n_(n), tcap_(tcap), seed_(seed), stream_(stream) {
+        if (n < 1 || n > 2147483647LL) throw std::invalid_argument("particle count must be in [1, 2^31)");
+        ntiles_ = (n + SCAN_TILE - 1) / SCAN_TILE;
+        for (int d = 0; d < D; ++d) { xa_[d] = dalloc<double>(n); xb_[d] = dalloc<double>(n); }
+        lw_ = dalloc<double>(n);
+        am_.zmask = dalloc<uint32_t>((n + 31) / 32 + 64);
+        am_.zbase = dalloc<uint32_t>((n + 31) / 32 + 64);
+        am_.surplus = dalloc<uint32_t>(n);
+        status_ = dalloc<unsigned long long>(3 * ntiles_);
+        ctrl_ = dalloc<Ctrl>(1);
+        tr_.lognc = dalloc<double>(tcap); tr_.ess = dalloc<double>(tcap);
+        tr_.resampled = dalloc<int>(tcap); tr_.obs = dalloc<double>(tcap * (NOBS > 0 ? NOBS : 1));
+        grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
+        grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
+        grid_scan_ = persistent_grid(k_resample_scan<SRC_LOGW, SYSTEMATIC>, SCAN_THREADS, n, SCAN_TILE);
+        int gmax = grid_init_ > grid_move_ ? grid_init_ : grid_move_;
+        partial_ = dalloc<double>((size_t)(4 + G + NOBS) * gmax);
+        SMCB_CUDA(cudaMemsetAsync(status_, 0, sizeof(unsigned long long) * 3 * ntiles_, stream_));
+        SetResampleParams(STRATIFIED, 0.5);  // reference defaults, sampler.h:259-267
+    }
+    ~Sampler() { for (void* p : allocs_) cudaFree(p); }
+    Sampler(const Sampler&) = delete;
+    Sampler& operator=(const Sampler&) = delete;
+
+    // sampler.h:885-893
+    void SetResampleParams(int mode, double threshold) {
+        mode_ = mode;
+        thr_ = threshold < 1 ? threshold * (double)n_ : threshold;
+    }
+    void SetParams(const typename Model::Params& p) { params_ = p; }
+    void SetSeed(unsigned long long seed) { seed_ = seed; }
+    // Injected randomness (parity testing): device pointers, reference consumption order.
+    void SetInjectedNoise(const double* znoise, const double* ures, const double* ustrat) { znoise_ = znoise; ures_ = ures; ustrat_ = ustrat; }
+
+    // sampler.h:481-550 (up to and including the resampling decision; the resampling pass itself is enqueued here too)
+    void Initialise() {
+        Ctrl h{};
+        h.thr = thr_; h.log_n = std::log((double)n_); h.parity = 1;  // init writes buffer A (dst of parity 1)
+        SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        StepArgs<Model> a = args();
+        if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
+        else k_step<Model, PHASE_INIT, false><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
+        SMCB_CUDA(cudaGetLastError());
+        enqueue_resample();
+        steps_ = 1;
+    }
+    // sampler.h:701-764
+    void Iterate() {
+        StepArgs<Model> a = args();
+        if (znoise_) k_step<Model, PHASE_MOVE, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        else k_step<Model, PHASE_MOVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        SMCB_CUDA(cudaGetLastError());
+        enqueue_resample();
+        ++steps_;
+    }
+    void IterateUntil(long long t_end) { while (steps_ - 1 < t_end) Iterate(); }
+    // Fused Integrate for the current (last) population: closes the observable trace.
+    void ObserveFinal() {
+        StepArgs<Model> a = args();
+        k_step<Model, PHASE_OBSERVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        SMCB_CUDA(cudaGetLastError());
+    }
+    long long kernel_launches_per_step() const { return 2; }
+
+    void Sync() { SMCB_CUDA(cudaStreamSynchronize(stream_)); }
+    Ctrl ReadCtrl() {
+        Ctrl h;
+        SMCB_CUDA(cudaMemcpyAsync(&h, ctrl_, sizeof h, cudaMemcpyDeviceToHost, stream_));
+        Sync();
+        return h;
+    }
+    // Copies the first `t` entries of the traces to host buffers (any pointer may be null).
+    void ReadTraces(long long t, double* lognc, double* ess, int* resampled, double* obs) {
+        if (lognc) SMCB_CUDA(cudaMemcpyAsync(lognc, tr_.lognc, sizeof(double) * t, cudaMemcpyDeviceToHost, stream_));
+        if (ess) SMCB_CUDA(cudaMemcpyAsync(ess, tr_.ess, sizeof(double) * t, cudaMemcpyDeviceToHost, stream_));
+        if (resampled) SMCB_CUDA(cudaMemcpyAsync(resampled, tr_.resampled, sizeof(int) * t, cudaMemcpyDeviceToHost, stream_));
+        if (obs && NOBS > 0) SMCB_CUDA(cudaMemcpyAsync(obs, tr_.obs, sizeof(double) * t * NOBS, cudaMemcpyDeviceToHost, stream_));
+        Sync();
+    }
+    // uRSIndices of the pending resampling (identity when the last step did not resample); sampler.h:190-192
+    void ReadAncestors(uint32_t* host_idx) {
+        Ctrl c = ReadCtrl();
+        uint32_t* d = dalloc_tmp<uint32_t>(n_);
+        if (c.resampled) {
+            k_decode_indices<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, d);
+            SMCB_CUDA(cudaGetLastError());
+            SMCB_CUDA(cudaMemcpyAsync(host_idx, d, sizeof(uint32_t) * n_, cudaMemcpyDeviceToHost, stream_));
+            Sync();
+        } else {
+            for (long long i = 0; i < n_; ++i) host_idx[i] = (uint32_t)i;
+        }
+        cudaFree(d);
+    }
+    long long GetNumber() const { return n_; }
+    cudaStream_t stream() const { return stream_; }
+    int grid_move() const { return grid_move_; }
+    int grid_scan() const { return grid_scan_; }
+
+private:
+    template <class T> T* dalloc(size_t count) {
+        void* p = nullptr;
+        SMCB_CUDA(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+        allocs_.push_back(p);
+        return (T*)p;
+    }
+    template <class T> T* dalloc_tmp(size_t count) {
+        void* p = nullptr;
+        SMCB_CUDA(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+        return (T*)p;
+    }
+    StepArgs<Model> args() {
+        StepArgs<Model> a;
+        for (int d = 0; d < D; ++d) { a.xa[d] = xa_[d]; a.xb[d] = xb_[d]; }
+        a.lw = lw_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
+        a.status = status_; a.nstatus = 3 * ntiles_; a.params = params_; a.seed = seed_;
+        a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_;
+        return a;
+    }
+    void enqueue_resample() {
+        ScanArgs s{};
+        s.in = lw_; s.n = n_; s.lse_ptr = &ctrl_->lse; s.enable_ptr = &ctrl_->resampled; s.u_ptr = &ctrl_->u_res;
+        s.ustrat = ustrat_; s.step_ptr = &ctrl_->T; s.seed = seed_; s.ticket = &ctrl_->ticket;
+        s.ws.statusA = status_; s.ws.statusB = status_ + ntiles_; s.ws.statusC = status_ + 2 * ntiles_;
+        s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
+        switch (mode_) {
+            case SYSTEMATIC: k_resample_scan<SRC_LOGW, SYSTEMATIC><<<grid_scan_, SCAN_THREADS, 0, stream_>>>(s); break;
+            case STRATIFIED: k_resample_scan<SRC_LOGW, STRATIFIED><<<grid_scan_, SCAN_THREADS, 0, stream_>>>(s); break;
+            default: throw std::invalid_argument("resampling mode not available in the fused engine yet");
+        }
+        SMCB_CUDA(cudaGetLastError());
+    }
+
+    long long n_, tcap_, ntiles_;
+    unsigned long long seed_;
+    cudaStream_t stream_;
+    int mode_ = STRATIFIED;
+    double thr_ = 0;
+    typename Model::Params params_{};
+    double* xa_[D];
+    double* xb_[D];
+    double* lw_ = nullptr;
+    AncestorMap am_{};
+    unsigned long long* status_ = nullptr;
+    Ctrl* ctrl_ = nullptr;
+    Traces tr_{};
+    double* partial_ = nullptr;
+    const double* znoise_ = nullptr;
+    const double* ures_ = nullptr;
+    const double* ustrat_ = nullptr;
+    int grid_init_ = 1, grid_move_ = 1, grid_scan_ = 1;
+    long long steps_ = 0;
+    std::vector<void*> allocs_;
+};
+
+}  // namespace smcb

@@ -1,0 +1,61 @@
+// Model functors for the device engine.  Each is the device restatement of one reference moveset
+// (user pfInitialise / pfMove virtuals, moveset.h:73-87) plus the integrands its driver feeds to
+// sampler::Integrate.  Functor contract (all static, __device__):
+//   D         doubles per particle state (stored as D SoA arrays)
+//   NZ_INIT   standard normals consumed by init(), NZ_MOVE by move() -- handed in as z[]
+//   init(x, lw, params, z)            pfInitialise: sets x and the initial log-weight
+//   move(t, x, lw, params, z)         pfMove at lTime = t: updates x, adds the incremental log-weight
+//   NSHIFT / shift_stat(x, h)         statistics whose pre-resample weighted means centre the fused moments
+//   NOBS / observe(x, shift, f)       integrands accumulated under the current weights (Integrate)
+//   finish_obs(v, shift, out)         weighted means v[] -> reported values
+// Arithmetic is written in the reference's operation order with contraction disabled (-fmad=false) so that,
+// on injected noise, states and log-weight increments are bit-identical to the CPU reference (only exp/log
+// in the normalisation differ by ulps).
+#pragma once
+#include "common.cuh"
+
+namespace smcb {
+
+// Nonlinear state-space model of Gordon, Salmond & Smith (1993): reference src/pfnonlinbs.cpp:35-120.
+struct NonlinBS {
+    static constexpr int D = 1;
+    static constexpr int NZ_INIT = 1;
+    static constexpr int NZ_MOVE = 1;
+    static constexpr int NSHIFT = 1;
+    static constexpr int NOBS = 2;
+    struct Params {
+        const double* y;      // observations y[0..T)
+        const double* cterm;  // 8 cos(1.2 t), particle-independent term of pfMove, tabulated on the host
+    };
+    // src/pfnonlinbs.cpp:35-42
+    static constexpr double var_x0 = 10.0, var_x = 10.0, var_y = 1.0, scale_y = 1.0 / 20.0;
+
+    __device__ static __forceinline__ double loglik(const Params& p, long long t, double x) {  // :86-88
+        double d = p.y[t] - x * x * scale_y;
+        return -0.5 * (d * d) / var_y;
+    }
+    __device__ static __forceinline__ void init(double (&x)[D], double& lw, const Params& p, const double* z) {  // :95-98
+        const double std_x0 = 3.1622776601683795;  // sqrt(10.0)
+        x[0] = 0.0 + std_x0 * z[0];
+        lw = loglik(p, 0, x[0]);
+    }
+    __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {  // :106-109
+        const double std_x = 3.1622776601683795;
+        double v = x[0];
+        v = 0.5 * v + 25.0 * v / (1.0 + v * v) + p.cterm[t] + (0.0 + std_x * z[0]);
+        x[0] = v;
+        lw += loglik(p, t, v);
+    }
+    __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[NSHIFT]) { h[0] = x[0]; }
+    // integrand_mean_x / integrand_var_x (:112-120), centred on `shift` instead of the not-yet-known mean
+    __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[NOBS]) {
+        double d = x[0] - shift[0];
+        f[0] = d; f[1] = d * d;
+    }
+    __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {
+        out[0] = shift[0] + v[0];        // mean
+        out[1] = v[1] - v[0] * v[0];     // E[(x - mean)^2]; the driver reports its square root
+    }
+};
+
+}  // namespace smcb

@@ -1,0 +1,199 @@
+"""ctypes access to the oracle (oracle/liboracle.so) and, when built, the compiled reference
+(oracle/_ref/libsmcref.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DP = ctypes.POINTER(ctypes.c_double)
+IP = ctypes.POINTER(ctypes.c_int)
+UP = ctypes.POINTER(ctypes.c_uint)
+L = ctypes.c_long
+D = ctypes.c_double
+
+MULTINOMIAL, RESIDUAL, STRATIFIED, SYSTEMATIC = 0, 1, 2, 3
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(DP)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        o = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        o.smco_lse.restype = D
+        o.smco_ess.restype = D
+        o.smco_integrate.restype = D
+        o.smco_time_pfnonlinbs.restype = D
+        for f in ("smco_counts_systematic", "smco_counts_stratified", "smco_counts_multinomial_iid", "smco_residual_floor"):
+            getattr(o, f).restype = L
+        _oracle = o
+    return _oracle
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsmcref.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        r = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsmcref.so"))
+        r.smcref_lse.restype = D
+        r.smcref_ess.restype = D
+        r.smcref_time_pfnonlinbs.restype = D
+        for f in ("smcref_pending_uniforms", "smcref_pending_normals", "smcref_consumed_uniforms", "smcref_consumed_normals"):
+            getattr(r, f).restype = L
+        _ref = r
+    return _ref
+
+
+# ---- oracle wrappers -----------------------------------------------------------------------------------
+def o_lse(lw):
+    lw = f64(lw)
+    return oracle().smco_lse(dp(lw), L(lw.size))
+
+
+def o_ess(lw):
+    lw = f64(lw)
+    return oracle().smco_ess(dp(lw), L(lw.size))
+
+
+def o_quantise(w):
+    w = f64(w)
+    out = np.empty_like(w)
+    oracle().smco_quantise_weights(dp(w), L(w.size), dp(out))
+    return out
+
+
+def o_normalised(lw):
+    lw = f64(lw)
+    out = np.empty_like(lw)
+    oracle().smco_normalised_weights(dp(lw), L(lw.size), dp(out))
+    return out
+
+
+def o_resample_w(mode, w, U=None, counts=None):
+    """(idx, counts) from normalised weights (oracle restatement of sampler.h:786-857)."""
+    n = (w if w is not None else counts).size
+    idx = np.empty(n, dtype=np.uint32)
+    cout = np.empty(n, dtype=np.int32)
+    Uu = None if U is None else f64(np.atleast_1d(U))
+    c = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+    rc = oracle().smco_resample_from_weights(mode, dp(None if w is None else f64(w)), L(n), dp(Uu), L(0 if Uu is None else Uu.size),
+                                             None if c is None else c.ctypes.data_as(IP), idx.ctypes.data_as(UP),
+                                             cout.ctypes.data_as(IP))
+    assert rc == 0
+    return idx, cout
+
+
+def o_resample_lw(mode, lw, U=None, counts=None):
+    lw = f64(lw)
+    n = lw.size
+    idx = np.empty(n, dtype=np.uint32)
+    cout = np.empty(n, dtype=np.int32)
+    Uu = None if U is None else f64(np.atleast_1d(U))
+    c = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+    rc = oracle().smco_resample(mode, dp(lw), L(n), dp(Uu), L(0 if Uu is None else Uu.size),
+                                None if c is None else c.ctypes.data_as(IP), idx.ctypes.data_as(UP), cout.ctypes.data_as(IP))
+    assert rc == 0
+    return idx, cout
+
+
+def sim_nonlin(T, seed, var_init=10.0, var_evol=10.0, var_obs=1.0, cos_offset=-1.0):
+    """Restated R/simNonlin.R (oracle/smc_oracle.c:smco_sim_nonlin) on numpy normals."""
+    rng = np.random.default_rng(seed)
+    zs, zo = rng.standard_normal(T), rng.standard_normal(T)
+    x, y = np.empty(T), np.empty(T)
+    oracle().smco_sim_nonlin(L(T), dp(zs), dp(zo), D(var_init), D(var_evol), D(var_obs), D(cos_offset), dp(x), dp(y))
+    return x, y
+
+
+def o_pfnonlinbs(y, N, mode, threshold, z=None, U=None, seed=0, want_idx=False):
+    y = f64(y)
+    T = y.size
+    mean, sd, nc, ess = np.empty(T), np.empty(T), np.empty(T), np.empty(T)
+    rs = np.empty(T, dtype=np.int32)
+    idx = np.empty((T, N), dtype=np.uint32) if want_idx else None
+    z = None if z is None else f64(z)
+    U = None if U is None else f64(U)
+    rc = oracle().smco_pfnonlinbs(dp(y), L(T), L(N), mode, D(threshold), dp(z), dp(U), ctypes.c_ulonglong(seed), dp(mean), dp(sd),
+                                  dp(nc), dp(ess), rs.ctypes.data_as(IP), None if idx is None else idx.ctypes.data_as(UP))
+    assert rc == 0
+    out = {"mean": mean, "sd": sd, "logNC": nc, "ESS": ess, "resampled": rs}
+    if want_idx:
+        out["idx"] = idx
+    return out
+
+
+# ---- compiled-reference wrappers ---------------------------------------------------------------------------
+def r_clear():
+    ref().smcref_clear_queues()
+
+
+def r_push(normals=None, uniforms=None, multinomial=None):
+    if normals is not None:
+        z = f64(normals)
+        ref().smcref_push_normals(dp(z), L(z.size))
+    if uniforms is not None:
+        u = f64(np.atleast_1d(uniforms))
+        ref().smcref_push_uniforms(dp(u), L(u.size))
+    if multinomial is not None:
+        c = np.ascontiguousarray(multinomial, dtype=np.int32)
+        ref().smcref_push_multinomial(c.ctypes.data_as(IP), L(c.size))
+
+
+def r_lse(lw):
+    lw = f64(lw)
+    return ref().smcref_lse(dp(lw), L(lw.size))
+
+
+def r_ess(lw):
+    lw = f64(lw)
+    return ref().smcref_ess(dp(lw), L(lw.size))
+
+
+def r_resample(mode, lw, uniforms=None, multinomial=None, weights_override=None):
+    """uRSIndices from the compiled reference's sampler::Resample."""
+    lw = f64(lw)
+    n = lw.size
+    r_clear()
+    r_push(uniforms=uniforms, multinomial=multinomial)
+    keep = None
+    if weights_override is not None:
+        keep = f64(weights_override)
+        ref().smcref_override_next_exp(dp(keep), L(n))
+    idx = np.empty(n, dtype=np.uint32)
+    val = np.empty(n)
+    ref().smcref_resample(mode, dp(lw), L(n), idx.ctypes.data_as(UP), dp(val))
+    return idx, val
+
+
+def r_pfnonlinbs(y, N, mode, threshold, z, U):
+    y = f64(y)
+    T = y.size
+    r_clear()
+    r_push(normals=z, uniforms=U)
+    mean, sd, nc, ess = np.empty(T), np.empty(T), np.empty(T), np.empty(T)
+    rs = np.empty(T, dtype=np.int32)
+    ref().smcref_pfnonlinbs(dp(y), L(T), L(N), mode, D(threshold), dp(mean), dp(sd), dp(nc), dp(ess), rs.ctypes.data_as(IP))
+    return {"mean": mean, "sd": sd, "logNC": nc, "ESS": ess, "resampled": rs}
+
+
+def random_weights(rng, n, spread=3.0, grid=True):
+    """Normalised weights from Gaussian log-weights; optionally on the engine's 2^-52 grid."""
+    lw = spread * rng.standard_normal(n)
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    return o_quantise(w) if grid else w
