@@ -92,6 +92,11 @@ int smcb200_pfNonlinBS_read(smcb200_pf* h, double* mean_host, double* sd_host, d
 int smcb200_pfNonlinBS_read_ancestors(smcb200_pf* h, unsigned int* idx_host);
 /* Kernel launches issued by the last run (for benchmark bookkeeping). */
 long smcb200_pfNonlinBS_launches(smcb200_pf* h);
+/* Per-kernel device timing: with profiling on, run() records one CUDA event after every launch; kernel_ms()
+ * then returns the summed duration and launch count of the propagate (k_step) and resampling (k_resample_scan)
+ * kernels of the last run (Initialise and the closing moment pass excluded). */
+int smcb200_pfNonlinBS_set_profile(smcb200_pf* h, int on);
+int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launches, float* scan_ms, long* scan_launches);
 int smcb200_pfNonlinBS_destroy(smcb200_pf* h);
 
 #ifdef __cplusplus

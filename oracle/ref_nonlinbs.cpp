@@ -46,9 +46,12 @@ long smcref_pending_uniforms(void) { return (long)shim::st().uq.size(); }
 long smcref_pending_normals(void) { return (long)shim::st().zq.size(); }
 long smcref_consumed_uniforms(void) { return shim::st().n_unif; }
 long smcref_consumed_normals(void) { return shim::st().n_norm; }
-// The next arma::exp() over a length-n vector returns w[] verbatim (used to feed the reference's
-// Resample identical normalised weights instead of exp(logw - LSE)).  The pointer must stay valid.
-void smcref_override_next_exp(const double* w, long n) { shim::st().exp_override = w; shim::st().exp_override_n = n; }
+// After `skip` further arma::exp() calls over length-n vectors, the next one returns w[] verbatim.  Used to feed
+// the reference's Resample identical normalised weights: in `cumsum(exp(lw - stableLogSumWeights(lw)))`
+// (sampler.h:811,833) the first exp belongs to stableLogSumWeights (skip = 1).  The pointer must stay valid.
+void smcref_override_exp(const double* w, long n, int skip) {
+    shim::st().exp_override = w; shim::st().exp_override_n = n; shim::st().exp_override_skip = skip;
+}
 
 // ---- engine primitives (reference population.h:46-50, sampler.h:413-417, :779-868) ------------
 double smcref_lse(const double* logw, long n) {

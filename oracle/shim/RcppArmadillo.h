@@ -47,8 +47,9 @@ struct State {
     std::deque<double> uq;                 // uniforms in [0,1)
     std::deque<double> zq;                 // standard normals
     std::deque<std::vector<int>> mq;       // multinomial count vectors
-    const double* exp_override = nullptr;  // one-shot replacement for the next arma::exp(vec) of matching length
+    const double* exp_override = nullptr;  // one-shot replacement for an upcoming arma::exp(vec) of matching length
     long exp_override_n = 0;
+    int exp_override_skip = 0;             // matching calls to let through first (e.g. the one inside stableLogSumWeights)
     long n_unif = 0, n_norm = 0, n_multinom = 0;  // consumption counters
 };
 inline State& st() { static State s; return s; }
@@ -145,7 +146,7 @@ inline vec operator-(const vec& a) { vec r(a.d.size()); for (size_t i = 0; i < a
 
 inline vec exp(const vec& a) {
     shim::State& s = shim::st();
-    if (s.exp_override && (long)a.d.size() == s.exp_override_n) {
+    if (s.exp_override && (long)a.d.size() == s.exp_override_n && s.exp_override_skip-- <= 0) {
         vec r(a.d.size());
         std::copy(s.exp_override, s.exp_override + s.exp_override_n, r.d.begin());
         s.exp_override = nullptr; s.exp_override_n = 0;

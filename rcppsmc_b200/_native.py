@@ -59,6 +59,9 @@ def lib():
     L.smcb200_pfNonlinBS_launches.argtypes = [ctypes.c_void_p]
     L.smcb200_pfNonlinBS_launches.restype = ctypes.c_long
     L.smcb200_pfNonlinBS_destroy.argtypes = [ctypes.c_void_p]
+    L.smcb200_pfNonlinBS_set_profile.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.smcb200_pfNonlinBS_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_long),
+                                               ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_long)]
     _lib = L
     return L
 
@@ -179,6 +182,16 @@ class PfNonlinBS:
         idx = np.empty(self.particles, dtype=np.uint32)
         _check(lib().smcb200_pfNonlinBS_read_ancestors(self._h, idx.ctypes.data_as(_c_uint_p)))
         return idx
+
+    def set_profile(self, on=True):
+        _check(lib().smcb200_pfNonlinBS_set_profile(self._h, 1 if on else 0))
+
+    def kernel_ms(self):
+        """(move_ms, move_launches, scan_ms, scan_launches) of the last profiled run."""
+        mv, sc = ctypes.c_float(), ctypes.c_float()
+        nm, ns = ctypes.c_long(), ctypes.c_long()
+        _check(lib().smcb200_pfNonlinBS_kernel_ms(self._h, ctypes.byref(mv), ctypes.byref(nm), ctypes.byref(sc), ctypes.byref(ns)))
+        return mv.value, nm.value, sc.value, ns.value
 
     def launches(self):
         return lib().smcb200_pfNonlinBS_launches(self._h)

@@ -105,6 +105,9 @@ struct smcb200_pf {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches = 0;
     std::vector<double> obs;
+    bool profile = false;
+    std::vector<cudaEvent_t> kev;  // per-launch events when profiling
+    size_t kev_used = 0;
 };
 
 extern "C" {
@@ -285,6 +288,15 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
                            resample_mode == SMCB200_SYSTEMATIC ? un : nullptr,
                            resample_mode == SMCB200_STRATIFIED ? un : nullptr);
         h->mode = resample_mode;
+        h->kev_used = 0;
+        if (h->profile) {
+            while (h->kev.size() < (size_t)(2 * h->T + 2)) { cudaEvent_t e; SMCB_CUDA(cudaEventCreate(&e)); h->kev.push_back(e); }
+            smcb200_pf* hp = h;
+            s.SetAfterLaunchHook([hp]() { if (hp->kev_used < hp->kev.size()) cudaEventRecord(hp->kev[hp->kev_used++], hp->stream); });
+            SMCB_CUDA(cudaEventRecord(h->kev[h->kev_used++], h->stream));
+        } else {
+            s.SetAfterLaunchHook(nullptr);
+        }
         SMCB_CUDA(cudaEventRecord(h->ev0, h->stream));
         s.Initialise();
         for (long t = 1; t < h->T; ++t) s.Iterate();
@@ -341,10 +353,35 @@ int smcb200_pfNonlinBS_read_ancestors(smcb200_pf* h, unsigned int* idx_host) {
 
 long smcb200_pfNonlinBS_launches(smcb200_pf* h) { return h ? h->launches : 0; }
 
+int smcb200_pfNonlinBS_set_profile(smcb200_pf* h, int on) {
+    if (!h) return fail(SMCB200_ERR_INVALID, "null handle");
+    h->profile = on != 0;
+    return SMCB200_OK;
+}
+
+int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launches, float* scan_ms, long* scan_launches) {
+    return guarded([&]() -> int {
+        if (!h || !move_ms || !move_launches || !scan_ms || !scan_launches) throw std::invalid_argument("null argument");
+        if (!h->ran || !h->profile || h->kev_used < 3) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: run with profiling enabled first");
+        SMCB_CUDA(cudaEventSynchronize(h->kev[h->kev_used - 1]));
+        // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1
+        double mv = 0, sc = 0; long nm = 0, ns = 0;
+        const size_t nint = h->kev_used - 1;
+        for (size_t i = 0; i < nint; ++i) {
+            float ms; SMCB_CUDA(cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]));
+            if (i == 0 || i == nint - 1) continue;           // init and the final moment pass are not counted
+            if (i % 2 == 1) { sc += ms; ++ns; } else { mv += ms; ++nm; }
+        }
+        *move_ms = (float)mv; *move_launches = nm; *scan_ms = (float)sc; *scan_launches = ns;
+        return SMCB200_OK;
+    });
+}
+
 int smcb200_pfNonlinBS_destroy(smcb200_pf* h) {
     if (!h) return SMCB200_OK;
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     delete h;
     return SMCB200_OK;
 }

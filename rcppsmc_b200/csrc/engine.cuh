@@ -12,6 +12,7 @@
 // out-of-place), one log-weight array; the reference's AoS std::vector<Space> + arma::vec
 // (population.h:53-112) is never materialised on the device.
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -331,6 +332,7 @@ public:
         if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
         else k_step<Model, PHASE_INIT, false><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
+        if (after_launch_) after_launch_();
         enqueue_resample();
         steps_ = 1;
     }
@@ -340,6 +342,7 @@ public:
         if (znoise_) k_step<Model, PHASE_MOVE, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         else k_step<Model, PHASE_MOVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
+        if (after_launch_) after_launch_();
         enqueue_resample();
         ++steps_;
     }
@@ -349,7 +352,10 @@ public:
         StepArgs<Model> a = args();
         k_step<Model, PHASE_OBSERVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
+        if (after_launch_) after_launch_();
     }
+    // Called after every kernel launch (per-kernel event timing in the benchmark).
+    void SetAfterLaunchHook(std::function<void()> f) { after_launch_ = std::move(f); }
     long long kernel_launches_per_step() const { return 2; }
 
     void Sync() { SMCB_CUDA(cudaStreamSynchronize(stream_)); }
@@ -418,6 +424,7 @@ private:
             default: throw std::invalid_argument("resampling mode not available in the fused engine yet");
         }
         SMCB_CUDA(cudaGetLastError());
+        if (after_launch_) after_launch_();
     }
 
     long long n_, tcap_, ntiles_;
@@ -439,6 +446,7 @@ private:
     const double* ustrat_ = nullptr;
     int grid_init_ = 1, grid_move_ = 1, grid_scan_ = 1;
     long long steps_ = 0;
+    std::function<void()> after_launch_;
     std::vector<void*> allocs_;
 };
 

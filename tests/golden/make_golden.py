@@ -1,0 +1,94 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference compiled against oracle/shim
+(oracle/_ref/libsmcref.so, built by `make -C oracle ref` from /root/reference).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors of its own, so these fixtures are outputs of
+the reference code itself on fixed, injected randomness.  They pin the oracle on machines where /root/reference
+is absent (the GPU box)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import helpers as H  # noqa: E402
+
+
+def main():
+    assert H.ref_available(), "build oracle/_ref first (make -C oracle ref)"
+    rng = np.random.default_rng(20251019)
+
+    # ---- 1. stableLogSumWeights / GetESS known answers (population.h:46-50, sampler.h:413-417)
+    out = {}
+    cases = [-np.sqrt(np.arange(1.0, 5.0))]  # skeleton example, inst/skeleton/rcppsmc_hello_world.Rd:29-32
+    for n in (1, 2, 3, 17, 256, 1000):
+        cases.append(4.0 * rng.standard_normal(n) - 300.0)
+    for i, lw in enumerate(cases):
+        out[f"lw{i}"] = lw
+        out[f"lse{i}"] = np.array(H.r_lse(lw))
+        out[f"ess{i}"] = np.array(H.r_ess(lw))
+    out["ncases"] = np.array(len(cases))
+    np.savez(os.path.join(HERE, "lse_kat.npz"), **out)
+
+    # ---- 2. sampler::Resample known answers (sampler.h:779-868)
+    out = {}
+    k = 0
+    # Appendix B of SURVEY.md (8 particles)
+    w8 = np.array([0.05, 0.30, 0.02, 0.20, 0.01, 0.25, 0.10, 0.07])
+    appb = [(H.SYSTEMATIC, [0.37], None), (H.STRATIFIED, [0.37, 0.91, 0.05, 0.50, 0.66, 0.12, 0.99, 0.25, 0.40], None),
+            (H.MULTINOMIAL, None, [0, 3, 0, 2, 0, 2, 1, 0])]
+    for mode, U, counts in appb:
+        idx, val = H.r_resample(mode, np.log(w8) + 3.0, uniforms=U, multinomial=counts)
+        out[f"mode{k}"] = np.array(mode); out[f"lw{k}"] = np.log(w8) + 3.0
+        out[f"U{k}"] = np.array(U if U is not None else []); out[f"counts{k}"] = np.array(counts if counts is not None else [], dtype=np.int32)
+        out[f"w{k}"] = np.array([]); out[f"idx{k}"] = idx
+        k += 1
+    for n in (1, 2, 5, 33, 257, 1000, 4097):
+        for mode in (H.SYSTEMATIC, H.STRATIFIED):
+            for spread in (1.0, 6.0):
+                lw = spread * rng.standard_normal(n)
+                U = rng.random(1 if mode == H.SYSTEMATIC else n + 1)
+                # (a) the reference's own path: weights = exp(lw - LSE)
+                idx, _ = H.r_resample(mode, lw, uniforms=U)
+                out[f"mode{k}"] = np.array(mode); out[f"lw{k}"] = lw; out[f"U{k}"] = U
+                out[f"counts{k}"] = np.array([], dtype=np.int32); out[f"w{k}"] = np.array([]); out[f"idx{k}"] = idx
+                k += 1
+                # (b) identical normalised weights on the 2^-52 grid fed to the reference's cumsum
+                w = H.random_weights(rng, n, spread)
+                idx, _ = H.r_resample(mode, lw, uniforms=U, weights_override=w)
+                out[f"mode{k}"] = np.array(mode); out[f"lw{k}"] = lw; out[f"U{k}"] = U
+                out[f"counts{k}"] = np.array([], dtype=np.int32); out[f"w{k}"] = w; out[f"idx{k}"] = idx
+                k += 1
+        # injected multinomial counts -> index map (sampler.h:846-857)
+        for total in (n, max(0, n - 1)):
+            counts = rng.multinomial(total, rng.dirichlet(np.full(n, 0.4))).astype(np.int32)
+            idx, _ = H.r_resample(H.MULTINOMIAL, np.zeros(n), multinomial=counts)
+            out[f"mode{k}"] = np.array(H.MULTINOMIAL); out[f"lw{k}"] = np.zeros(n); out[f"U{k}"] = np.array([])
+            out[f"counts{k}"] = counts; out[f"w{k}"] = np.array([]); out[f"idx{k}"] = idx
+            k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "resample_kat.npz"), **out)
+
+    # ---- 3. pfNonlinBS traces from the reference sampler + nonlinbs_move on injected draws
+    out = {}
+    k = 0
+    for (N, T, mode, thr) in ((200, 20, H.SYSTEMATIC, 1.01 * 200), (200, 20, H.STRATIFIED, 1.01 * 200), (64, 12, H.SYSTEMATIC, 0.5),
+                              (1, 4, H.SYSTEMATIC, 1.01), (3, 6, H.STRATIFIED, 1.01 * 3)):
+        _, y = H.sim_nonlin(T, 100 + k)
+        z = rng.standard_normal(N * T)
+        U = rng.random(T * (N + 1))
+        r = H.r_pfnonlinbs(y, N, mode, thr, z, U)
+        out[f"N{k}"] = np.array(N); out[f"T{k}"] = np.array(T); out[f"mode{k}"] = np.array(mode); out[f"thr{k}"] = np.array(thr)
+        out[f"y{k}"] = y; out[f"z{k}"] = z; out[f"U{k}"] = U
+        for key in ("mean", "sd", "logNC", "ESS", "resampled"):
+            out[f"{key}{k}"] = r[key]
+        k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "pfnonlinbs_kat.npz"), **out)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,7 +173,7 @@ def r_resample(mode, lw, uniforms=None, multinomial=None, weights_override=None)
     keep = None
     if weights_override is not None:
         keep = f64(weights_override)
-        ref().smcref_override_next_exp(dp(keep), L(n))
+        ref().smcref_override_exp(dp(keep), L(n), 1)
     idx = np.empty(n, dtype=np.uint32)
     val = np.empty(n)
     ref().smcref_resample(mode, dp(lw), L(n), idx.ctypes.data_as(UP), dp(val))
