@@ -22,7 +22,7 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get("SMCB200_LIB", _build.LIB)  # override only for kernel experiments
 
 
 def lib():

@@ -164,7 +164,7 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
         if (!idx_out_host) throw std::invalid_argument("smcb200_resample: idx_out required");
         if (mode < 0 || mode > 3) throw std::invalid_argument("smcb200_resample: unknown resampling mode");
         require_device();
-        const long long ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+        const long long ntiles = scan_tiles(n);
         DevBuf zmask(sizeof(uint32_t) * ((n + 31) / 32 + 64)), zbase(sizeof(uint32_t) * ((n + 31) / 32 + 64));
         DevBuf surplus(sizeof(uint32_t) * n), status(sizeof(unsigned long long) * 3 * ntiles);
         DevBuf misc(sizeof(unsigned) * 4 + sizeof(double) * 2), idx(sizeof(uint32_t) * n), counts(sizeof(int) * n);
@@ -198,15 +198,13 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
             if (mode == SMCB200_SYSTEMATIC) {
                 if (!uniforms_host || n_uniforms < 1) throw std::invalid_argument("smcb200_resample: SYSTEMATIC needs 1 uniform");
                 SMCB_CUDA(cudaMemcpy(u_dev, uniforms_host, sizeof(double), cudaMemcpyHostToDevice));
-                int grid = persistent_grid(k_resample_scan<SRC_WEIGHTS, SYSTEMATIC>, SCAN_THREADS, n, SCAN_TILE);
-                k_resample_scan<SRC_WEIGHTS, SYSTEMATIC><<<grid, SCAN_THREADS>>>(a);
+                launch_resample_scan<SRC_WEIGHTS, SYSTEMATIC>(a, 0);
             } else if (mode == SMCB200_STRATIFIED) {
                 if (!uniforms_host || n_uniforms < n + 1) throw std::invalid_argument("smcb200_resample: STRATIFIED needs n+1 uniforms");
                 us = DevBuf(sizeof(double) * (n + 1));
                 SMCB_CUDA(cudaMemcpy(us.p, uniforms_host, sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
                 a.ustrat = us.as<double>();
-                int grid = persistent_grid(k_resample_scan<SRC_WEIGHTS, STRATIFIED>, SCAN_THREADS, n, SCAN_TILE);
-                k_resample_scan<SRC_WEIGHTS, STRATIFIED><<<grid, SCAN_THREADS>>>(a);
+                launch_resample_scan<SRC_WEIGHTS, STRATIFIED>(a, 0);
             } else {
                 throw std::invalid_argument("smcb200_resample: MULTINOMIAL / RESIDUAL need counts_in in this build");
             }
@@ -352,6 +350,13 @@ int smcb200_pfNonlinBS_read_ancestors(smcb200_pf* h, unsigned int* idx_host) {
 }
 
 long smcb200_pfNonlinBS_launches(smcb200_pf* h) { return h ? h->launches : 0; }
+
+#ifdef SMCB_PROFILE_LOOKBACK
+void smcb200_dbg_lookback_stats(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, smcb::g_lb_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(smcb::g_lb_stats, z, sizeof z); }
+}
+#endif
 
 int smcb200_pfNonlinBS_set_profile(smcb200_pf* h, int on) {
     if (!h) return fail(SMCB200_ERR_INVALID, "null handle");

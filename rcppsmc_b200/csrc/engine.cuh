@@ -12,6 +12,7 @@
 // out-of-place), one log-weight array; the reference's AoS std::vector<Space> + arma::vec
 // (population.h:53-112) is never materialised on the device.
 #pragma once
+#include <cstdlib>
 #include <functional>
 #include <vector>
 
@@ -103,28 +104,76 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
 #pragma unroll
     for (int j = 0; j < NOBS; ++j) obs[j] = 0.0;
 
+    // ---- particle loop, software-pipelined: the ancestor decode is a chain of three dependent loads
+    // (bitmap word -> surplus entry -> parent state), so each link is issued one iteration ahead of its use:
+    //   stage A (pair p+3S)  bitmap word + rank base          stage B (pair p+2S)  rank -> surplus loads
+    //   stage C (pair p+S)   parent state (and stored log-weight when the last step did not resample)
+    //   compute (pair p)     moments, RNG, model functor, stores, online log-sum-exp
     const long long npairs = (n + 1) >> 1;
-    for (long long p = (long long)blockIdx.x * STEP_THREADS + tid; p < npairs; p += (long long)gridDim.x * STEP_THREADS) {
+    const long long stride = (long long)gridDim.x * STEP_THREADS;
+    const long long p0 = (long long)blockIdx.x * STEP_THREADS + tid;
+    uint32_t mA = 0u, bA = 0u;                 // stage A result
+    uint32_t ancB[2] = {0u, 0u};               // stage B result
+    double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result
+    auto stageA = [&](long long p) {
+        if (PHASE != PHASE_INIT && resampled && p < npairs) {
+            mA = __ldg(a.am.zmask + (p >> 4));
+            bA = __ldg(a.am.zbase + (p >> 4));
+        }
+    };
+    auto stageB = [&](long long p) {   // consumes mA/bA (loaded for this p one iteration ago)
+        if (PHASE != PHASE_INIT && p < npairs) {
+            const long long s0 = 2 * p;
+            ancB[0] = (uint32_t)s0; ancB[1] = (uint32_t)(s0 + 1);
+            if (resampled) {
+                const uint32_t bit = (uint32_t)s0 & 31u;
+                const uint32_t below = mA & ((1u << bit) - 1u);
+                const uint32_t rank = bA + __popc(below);
+                const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
+                if (z0) ancB[0] = __ldg(a.am.surplus + rank);
+                if (z1) ancB[1] = __ldg(a.am.surplus + rank + z0);
+            }
+        }
+    };
+    auto stageC = [&](long long p) {   // consumes ancB
+        if (PHASE != PHASE_INIT && p < npairs) {
+            const long long s0 = 2 * p;
+            const bool has1 = s0 + 1 < n;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                xC[0][d] = src[d][ancB[0]];
+                xC[1][d] = has1 ? src[d][ancB[1]] : 0.0;
+            }
+            if (!resampled) { lwC[0] = a.lw[s0]; lwC[1] = has1 ? a.lw[s0 + 1] : 0.0; }
+        }
+    };
+    // prologue: fill the pipeline
+    stageA(p0); stageB(p0); stageC(p0);
+    stageA(p0 + stride); stageB(p0 + stride);
+    stageA(p0 + 2 * stride);
+
+    for (long long p = p0; p < npairs; p += stride) {
         const long long s0 = 2 * p;
         const bool has1 = s0 + 1 < n;
         double x[2][D], lwv[2];
-        // ---- gather the previous population (sampler.h:860-864 replication, fused)
         if (PHASE != PHASE_INIT) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                long long s = s0 + h;
-                if (h == 1 && !has1) break;
-                long long anc = s;
-                double lwp;
-                if (resampled) { anc = decode_ancestor(a.am, s); lwp = -log_n; }
-                else lwp = a.lw[s] - lse_prev;
 #pragma unroll
-                for (int d = 0; d < D; ++d) x[h][d] = src[d][anc];
-                lwv[h] = lwp;
-                if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
+                for (int d = 0; d < D; ++d) x[h][d] = xC[h][d];
+                lwv[h] = resampled ? -log_n : lwC[h] - lse_prev;
+            }
+            // advance the pipeline before the arithmetic of this pair
+            stageC(p + stride);
+            stageB(p + 2 * stride);
+            stageA(p + 3 * stride);
+            if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !has1) break;
                     double f[NOBS > 0 ? NOBS : 1];
                     Model::observe(x[h], shift, f);
-                    double w = resampled ? 1.0 : exp(lwp);
+                    double w = resampled ? 1.0 : exp(lwv[h]);
                     obs0 += w;
 #pragma unroll
                     for (int j = 0; j < NOBS; ++j) obs[j] = fma(w, f[j], obs[j]);
@@ -291,7 +340,7 @@ public:
     Sampler(long long n, long long tcap, unsigned long long seed, cudaStream_t stream = 0)
         : n_(n), tcap_(tcap), seed_(seed), stream_(stream) {
         if (n < 1 || n > 2147483647LL) throw std::invalid_argument("particle count must be in [1, 2^31)");
-        ntiles_ = (n + SCAN_TILE - 1) / SCAN_TILE;
+        ntiles_ = scan_tiles(n);
         for (int d = 0; d < D; ++d) { xa_[d] = dalloc<double>(n); xb_[d] = dalloc<double>(n); }
         lw_ = dalloc<double>(n);
         am_.zmask = dalloc<uint32_t>((n + 31) / 32 + 64);
@@ -303,7 +352,7 @@ public:
         tr_.resampled = dalloc<int>(tcap); tr_.obs = dalloc<double>(tcap * (NOBS > 0 ? NOBS : 1));
         grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
         grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
-        grid_scan_ = persistent_grid(k_resample_scan<SRC_LOGW, SYSTEMATIC>, SCAN_THREADS, n, SCAN_TILE);
+        grid_scan_ = resample_scan_grid<SRC_LOGW, SYSTEMATIC>(n);
         int gmax = grid_init_ > grid_move_ ? grid_init_ : grid_move_;
         partial_ = dalloc<double>((size_t)(4 + G + NOBS) * gmax);
         SMCB_CUDA(cudaMemsetAsync(status_, 0, sizeof(unsigned long long) * 3 * ntiles_, stream_));
@@ -418,9 +467,10 @@ private:
         s.ustrat = ustrat_; s.step_ptr = &ctrl_->T; s.seed = seed_; s.ticket = &ctrl_->ticket;
         s.ws.statusA = status_; s.ws.statusB = status_ + ntiles_; s.ws.statusC = status_ + 2 * ntiles_;
         s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
+        { const char* e = getenv("SMCB200_DBG"); s.dbg = e ? atoi(e) : 0; }
         switch (mode_) {
-            case SYSTEMATIC: k_resample_scan<SRC_LOGW, SYSTEMATIC><<<grid_scan_, SCAN_THREADS, 0, stream_>>>(s); break;
-            case STRATIFIED: k_resample_scan<SRC_LOGW, STRATIFIED><<<grid_scan_, SCAN_THREADS, 0, stream_>>>(s); break;
+            case SYSTEMATIC: launch_resample_scan<SRC_LOGW, SYSTEMATIC>(s, stream_); break;
+            case STRATIFIED: launch_resample_scan<SRC_LOGW, STRATIFIED>(s, stream_); break;
             default: throw std::invalid_argument("resampling mode not available in the fused engine yet");
         }
         SMCB_CUDA(cudaGetLastError());

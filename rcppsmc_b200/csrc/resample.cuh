@@ -17,7 +17,13 @@
 
 namespace smcb {
 
-constexpr int SCAN_THREADS = 256;
+#ifndef SMCB_SCAN_THREADS
+#define SMCB_SCAN_THREADS 256
+#endif
+#ifndef SMCB_SCAN_MINB
+#define SMCB_SCAN_MINB 3
+#endif
+constexpr int SCAN_THREADS = SMCB_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 slots per tile
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
@@ -51,7 +57,19 @@ struct ScanWs {
     unsigned long long* statusC;  // [ntiles] surplus chain (count-map kernel only)
 };
 
-// Exclusive prefix of `agg` over tiles [0, tile) by decoupled look-back.  Called by all 32 lanes of warp 0.
+// Exclusive prefix of `agg` over tiles [0, tile) by decoupled look-back.  Called by all 32 lanes of one warp.
+// Each round keeps LB_DEPTH status words per lane in flight (a 32*LB_DEPTH-tile window per L2 round trip) and the
+// lanes accumulate privately; the only cross-lane reduction happens once, after the nearest full prefix is found.
+#ifndef SMCB_LB_DEPTH
+#define SMCB_LB_DEPTH 4
+#endif
+#ifndef SMCB_LB_SLEEP
+#define SMCB_LB_SLEEP 0
+#endif
+constexpr int LB_DEPTH = SMCB_LB_DEPTH;
+#ifdef SMCB_PROFILE_LOOKBACK
+__device__ unsigned long long g_lb_stats[8];  // [0] cycles, [1] rounds, [2] calls, [3] stalled polls (experiment build)
+#endif
 __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsigned long long* status, int tile,
                                                                  unsigned long long agg) {
     const int lane = threadIdx.x & 31;
@@ -60,40 +78,124 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsign
         return 0ull;
     }
     if (lane == 0) status[tile] = ST_AGG | agg;
-    unsigned long long excl = 0ull;
+    unsigned long long acc = 0ull;
     int base = tile - 1;
-    while (true) {
-        int idx = base - lane;
-        unsigned long long v = ST_PRE;  // virtual predecessors of tile 0: prefix 0
-        if (idx >= 0) v = status[idx];
-        while (__any_sync(SMCB_FULL, (v >> 62) == 0ull)) {
-            if (idx >= 0 && (v >> 62) == 0ull) v = status[idx];
-        }
-        unsigned pm = __ballot_sync(SMCB_FULL, (v >> 62) == 2ull);
-        int first = pm ? (__ffs(pm) - 1) : 31;
-        unsigned long long c = (lane <= first) ? (v & ST_VAL) : 0ull;
+    bool done = false;
+#ifdef SMCB_PROFILE_LOOKBACK
+    long long t0 = clock64(); unsigned rounds = 0, stalled = 0;
+#endif
+    while (!done) {
+#ifdef SMCB_PROFILE_LOOKBACK
+        ++rounds;
+#endif
+        unsigned long long v[LB_DEPTH];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(SMCB_FULL, c, o);
-        excl += c;
-        if (pm) break;
-        base -= 32;
+        for (int r = 0; r < LB_DEPTH; ++r) {
+            int idx = base - 32 * r - lane;
+            v[r] = 2ull << 62;  // virtual predecessors of tile 0: prefix 0
+            if (idx >= 0) v[r] = status[idx];
+        }
+#pragma unroll
+        for (int r = 0; r < LB_DEPTH; ++r) {
+            if (done) break;
+            if (__any_sync(SMCB_FULL, (v[r] >> 62) == 0ull)) {        // window not published yet: poll again from here
+                if (SMCB_LB_SLEEP > 0) __nanosleep(SMCB_LB_SLEEP);
+#ifdef SMCB_PROFILE_LOOKBACK
+                ++stalled;
+#endif
+                break;
+            }
+            unsigned pm = __ballot_sync(SMCB_FULL, (v[r] >> 62) == 2ull);
+            int first = pm ? (__ffs(pm) - 1) : 31;
+            if (lane <= first) acc += v[r] & ST_VAL;
+            base -= 32;
+            if (pm) done = true;
+        }
     }
-    if (lane == 0) status[tile] = ST_PRE | (excl + agg);
-    return excl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCB_FULL, acc, o);
+    if (lane == 0) status[tile] = ST_PRE | (acc + agg);
+#ifdef SMCB_PROFILE_LOOKBACK
+    if (lane == 0) {
+        atomicAdd(&g_lb_stats[0], (unsigned long long)(clock64() - t0)); atomicAdd(&g_lb_stats[1], (unsigned long long)rounds);
+        atomicAdd(&g_lb_stats[2], 1ull); atomicAdd(&g_lb_stats[3], (unsigned long long)stalled);
+    }
+#endif
+    return acc;
+}
+
+// Same, for a tile whose aggregate was published earlier (pipelined kernel): walks the predecessors, then publishes the
+// inclusive prefix.  Returns the exclusive prefix.
+__device__ __forceinline__ unsigned long long lookback_resolve(volatile unsigned long long* status, int tile, unsigned long long agg) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) return 0ull;
+    unsigned long long acc = 0ull;
+    int base = tile - 1;
+    bool done = false;
+#ifdef SMCB_PROFILE_LOOKBACK
+    long long t0 = clock64(); unsigned rounds = 0, stalled = 0;
+#endif
+    while (!done) {
+#ifdef SMCB_PROFILE_LOOKBACK
+        ++rounds;
+#endif
+        unsigned long long v[LB_DEPTH];
+#pragma unroll
+        for (int r = 0; r < LB_DEPTH; ++r) {
+            int idx = base - 32 * r - lane;
+            v[r] = 2ull << 62;  // virtual predecessors of tile 0: prefix 0
+            if (idx >= 0) v[r] = status[idx];
+        }
+#pragma unroll
+        for (int r = 0; r < LB_DEPTH; ++r) {
+            if (done) break;
+            if (__any_sync(SMCB_FULL, (v[r] >> 62) == 0ull)) {        // window not published yet: poll again from here
+#ifdef SMCB_PROFILE_LOOKBACK
+                ++stalled;
+#endif
+                break;
+            }
+            unsigned pm = __ballot_sync(SMCB_FULL, (v[r] >> 62) == 2ull);
+            int first = pm ? (__ffs(pm) - 1) : 31;
+            if (lane <= first) acc += v[r] & ST_VAL;
+            base -= 32;
+            if (pm) done = true;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCB_FULL, acc, o);
+    if (lane == 0) status[tile] = ST_PRE | (acc + agg);
+#ifdef SMCB_PROFILE_LOOKBACK
+    if (lane == 0) {
+        atomicAdd(&g_lb_stats[0], (unsigned long long)(clock64() - t0)); atomicAdd(&g_lb_stats[1], (unsigned long long)rounds);
+        atomicAdd(&g_lb_stats[2], 1ull); atomicAdd(&g_lb_stats[3], (unsigned long long)stalled);
+    }
+#endif
+    return acc;
+}
+
+// Exact u64 (< 2^53) -> double without the XU-pipe I2F: two magic-number halves and one fused multiply-add.
+__device__ __forceinline__ double u64_to_double_exact(unsigned long long v) {
+    double hi = __hiloint2double(0x43300000, (int)(v >> 32)) - TWO52;
+    double lo = __hiloint2double(0x43300000, (int)(unsigned)v) - TWO52;
+    return fma(hi, 4294967296.0, lo);
 }
 
 // #{ j in [0,n) : fl((double)j/(double)n) < v } -- the number of children the reference's two-pointer loop has
 // handed out once the cumulative weight reaches W with v = fl(W - u) (sampler.h:814,836).
 __device__ __forceinline__ long long children_below(double v, long long n, double nd, bool pow2) {
     if (!(v > 0.0)) return 0;
-    double g = v * nd;
-    double c = ceil(g);
-    if (c >= nd) {
+    double g = v * nd;                       // exact when n is a power of two
+    if (g >= nd) {
         if (pow2 || g - nd >= 9.5367431640625e-07) return n;
-    } else if (pow2 || fabs(g - rint(g)) >= 9.5367431640625e-07) {
-        return (long long)c;  // exact when n is a power of two; otherwise safely away from a rounding tie
+    } else {
+        // ceil(g) for 0 < g < 2^31 without F2I/FRND: round to nearest through the 2^52 magic constant
+        double t = g + TWO52;
+        double r = t - TWO52;
+        long long c = (long long)(unsigned)__double2loint(t) + (r < g ? 1 : 0);
+        if (pow2 || fabs(g - r) >= 9.5367431640625e-07) return c;  // safely away from a rounding tie
     }
-    long long j = (long long)fmin(c, nd);
+    long long j = (long long)fmin(ceil(g), nd);
     while (j < n && ((double)j / nd) < v) ++j;
     while (j > 0 && !(((double)(j - 1) / nd) < v)) --j;
     return j;
@@ -113,6 +215,7 @@ struct ScanArgs {
     AncestorMap am;
     int* count_out;           // optional: children counts per parent
     unsigned int* tail_info;  // optional [2]: {sum of counts, number of zero-count slots}
+    int dbg;                  // experiment switches (0 in production): 1 skip look-back A, 2 skip look-back B, 4 skip exp, 8 skip surplus
 };
 
 enum { SRC_LOGW = 0, SRC_WEIGHTS = 1 };
@@ -120,7 +223,7 @@ enum { SRC_LOGW = 0, SRC_WEIGHTS = 1 };
 template <int MODE>
 __device__ __forceinline__ long long children_upto(unsigned long long cum, const ScanArgs& a, double nd, double inv_n,
                                                    double dRand, bool pow2, long long step) {
-    double W = (double)cum * INV_TWO52;  // exact: cum < 2^53
+    double W = u64_to_double_exact(cum) * INV_TWO52;  // exact: cum < 2^53
     if (MODE == SYSTEMATIC) {
         return children_below(W - dRand, a.n, nd, pow2);
     } else {
@@ -150,17 +253,86 @@ __device__ __forceinline__ long long children_upto(unsigned long long cum, const
     }
 }
 
-// One pass: weights -> (zmask, zbase, surplus).  Persistent blocks pull tiles from a ticket counter.
+// Surplus writers shared by the resampling kernels: parent `gk` owns surplus[E .. E+e).  Runs of up to SURPLUS_SMALL
+// are written by the owning lane; longer ones are finished by the whole warp (write_surplus_heavy, cold path,
+// 16-byte stores for the aligned middle of very long runs).
+constexpr int SURPLUS_SMALL = 8;
+__device__ __forceinline__ void write_surplus_small(uint32_t* __restrict__ surplus, long long E, int e, uint32_t gk, long long cap) {
+    if (e > 0) {
+        int small = e < SURPLUS_SMALL ? e : SURPLUS_SMALL;
+        for (int r = 0; r < small; ++r) if (E + r < cap) surplus[E + r] = gk;
+    }
+}
+__device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ surplus, long long hE, long long hend, uint32_t hk, long long cap) {
+    const int lane = threadIdx.x & 31;
+    if (hend > cap) hend = cap;
+    if (hend - hE >= 1024) {
+        long long a0 = (hE + 3) & ~3ll, a1 = hend & ~3ll;
+        for (long long r = hE + lane; r < a0; r += 32) surplus[r] = hk;
+        uint4 v = make_uint4(hk, hk, hk, hk);
+        for (long long r = a0 + 4 * lane; r < a1; r += 128) *reinterpret_cast<uint4*>(surplus + r) = v;
+        for (long long r = a1 + lane; r < hend; r += 32) surplus[r] = hk;
+    } else {
+        for (long long r = hE + lane; r < hend; r += 32) surplus[r] = hk;
+    }
+}
+// Warp-cooperative completion of the runs flagged in `hbits` (bit k <=> item k of this lane has e > SURPLUS_SMALL).
+// E[k], e[k] are recomputed from the lane's running values in this rarely taken path.
+template <int ITEMS>
+__device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus, unsigned hbits, const int (&cnt)[ITEMS],
+                                                  long long cfirst, long long zexcl, unsigned zbits, long long g0, long long cap) {
+    const int lane = threadIdx.x & 31;
+    unsigned any;
+    while ((any = __ballot_sync(SMCB_FULL, hbits != 0u)) != 0u) {
+        const int src = __ffs(any) - 1;
+        long long hE = 0, hend = 0;
+        uint32_t hk = 0;
+        if (lane == src) {
+            const int kk = __ffs(hbits) - 1;
+            hbits &= hbits - 1;
+            long long ck1 = cfirst, zk = zexcl;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                if (k == kk) { hE = ck1 - (g0 + k) + zk + SURPLUS_SMALL; hend = hE + (cnt[k] - 1 - SURPLUS_SMALL); hk = (uint32_t)(g0 + k); }
+                ck1 += cnt[k];
+                zk += (zbits >> k) & 1u;
+            }
+        }
+        hE = __shfl_sync(SMCB_FULL, hE, src);
+        hend = __shfl_sync(SMCB_FULL, hend, src);
+        hk = __shfl_sync(SMCB_FULL, hk, src);
+        write_surplus_heavy(surplus, hE, hend, hk, cap);
+    }
+}
+
+inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+// One pass: weights -> (zmask, zbase, surplus).  Persistent blocks pull 2048-slot tiles from a ticket counter and keep
+// THREE tiles in flight, one per pipeline stage, so that neither look-back chain is ever waited on right after its
+// aggregate was published (measured: un-pipelined, each look-back stalled ~10k cycles on predecessors that had not
+// reached their publish point yet):
+//   S1(tile t+2)  coalesced load, quantise to the 2^-52 grid, block scan, publish the weight-mass aggregate
+//   S2(tile t+1)  look-back A (published a full iteration ago) -> children counts -> publish the zero-slot aggregate
+//   S3(tile t)    look-back B (published a full iteration ago) -> zero-slot bitmap + surplus lists
+// Stage state lives in shared memory (double-buffered), not registers.
+constexpr int SCAN_PAD = SCAN_TILE + SCAN_TILE / SCAN_ITEMS;   // blocked layout with one pad word per thread
+struct ScanSmem {
+    unsigned long long cum[2][SCAN_PAD];   // S1 -> S2: tile-relative inclusive mass per slot (pad word: unused)
+    int c[2][SCAN_PAD];                    // S2 -> S3: children handed out up to each slot; pad word = value before the thread's run
+    int zrel[2][SCAN_THREADS];             // S2 -> S3: zero-count slots before the thread's run, tile-relative
+    unsigned long long warp_tot[SCAN_WARPS];
+    int warp_z[SCAN_WARPS];
+    unsigned long long bcast[2];
+    long long zpre;
+    int tile[3];
+};
+constexpr size_t SCAN_SMEM_BYTES = sizeof(ScanSmem);
+
 template <int SRC, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) k_resample_scan(ScanArgs a) {
+__global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(ScanArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
-    __shared__ unsigned long long s_q[SCAN_TILE + SCAN_TILE / 8];
-    __shared__ unsigned long long s_warp[SCAN_WARPS];
-    __shared__ int s_warpz[SCAN_WARPS];
-    __shared__ unsigned long long s_bcast[2];
-    __shared__ int s_tile;
-    __shared__ unsigned int s_heavy_n;
-    __shared__ unsigned int s_heavy[3 * 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n = a.n;
@@ -172,160 +344,195 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resample_scan(ScanArgs a) {
     const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
 
-    while (true) {
-        if (tid == 0) { s_tile = (int)atomicAdd(a.ticket, 1u); s_heavy_n = 0; }
+    // tiles held by the stages: t1 enters S1 this iteration, t2 is in S2, t3 in S3 (-1 = empty)
+    int t2 = -1, t3 = -1;
+    for (int it = 0;; ++it) {
+        const int b1 = it & 1, b2 = b1 ^ 1;   // cum buffer written by S1 / read by S2; c buffer written by S2 = b2, read by S3 = b1
+        if (tid == 0) S.tile[0] = (int)atomicAdd(a.ticket, 1u);
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) break;
-        const long long base = (long long)tile * SCAN_TILE;
+        int t1 = S.tile[0];
+        if (t1 >= ntiles) t1 = -1;
+        if (t1 < 0 && t2 < 0 && t3 < 0) break;
 
-        // ---- striped (coalesced) load, quantise, transpose to a blocked arrangement through shared memory
+        // ================= S1: load, quantise, block scan, publish aggregate =================
+        if (t1 >= 0) {
+            const long long base = (long long)t1 * SCAN_TILE;
+            unsigned long long* sq = S.cum[b1];
 #pragma unroll
-        for (int r = 0; r < SCAN_ITEMS; ++r) {
-            int i = r * SCAN_THREADS + tid;
-            long long gi = base + i;
-            unsigned long long q = 0ull;
-            if (gi < n) {
-                double w = (SRC == SRC_LOGW) ? exp(a.in[gi] - lse) : a.in[gi];
-                q = (unsigned long long)__double2ll_rn(w * TWO52);
+            for (int r = 0; r < SCAN_ITEMS; ++r) {
+                int i = r * SCAN_THREADS + tid;
+                long long gi = base + i;
+                unsigned long long q = 0ull;
+                if (gi < n) {
+                    double w = (SRC == SRC_LOGW) ? exp(a.in[gi] - lse) : a.in[gi];
+                    q = (unsigned long long)__double2ll_rn(w * TWO52);
+                }
+                sq[i + (i >> 3)] = q;
             }
-            s_q[i + (i >> 3)] = q;
-        }
-        __syncthreads();
-        unsigned long long cum[SCAN_ITEMS];
-        {
-            unsigned long long run = 0ull;
+            __syncthreads();
+            unsigned long long cum[SCAN_ITEMS];
+            {
+                unsigned long long run = 0ull;
 #pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) { run += s_q[tid * (SCAN_ITEMS + 1) + k]; cum[k] = run; }
-        }
-        // ---- block scan of thread totals
-        unsigned long long tot = cum[SCAN_ITEMS - 1];
-        unsigned long long inc = tot;
+                for (int k = 0; k < SCAN_ITEMS; ++k) { run += sq[tid * (SCAN_ITEMS + 1) + k]; cum[k] = run; }
+            }
+            const unsigned long long tot = cum[SCAN_ITEMS - 1];
+            unsigned long long inc = tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(SMCB_FULL, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        unsigned long long warp_off = 0ull, tile_agg = 0ull;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(SMCB_FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) S.warp_tot[warp] = inc;
+            __syncthreads();
+            unsigned long long off = inc - tot, agg = 0ull;
 #pragma unroll
-        for (int w = 0; w < SCAN_WARPS; ++w) { unsigned long long v = s_warp[w]; if (w < warp) warp_off += v; tile_agg += v; }
-        if (warp == 0) {
-            unsigned long long ex = lookback_exclusive(a.ws.statusA, tile, tile_agg);
-            if (lane == 0) s_bcast[0] = ex;
-        }
-        __syncthreads();
-        const unsigned long long thread_excl = s_bcast[0] + warp_off + (inc - tot);
-
-        // ---- children counts from the closed form, zero-slot flags
-        long long cprev = children_upto<MODE>(thread_excl, a, nd, inv_n, dRand, pow2, step);
-        const long long cfirst = cprev;
-        int cnt[SCAN_ITEMS];
-        unsigned zbits = 0u;
-        const long long g0 = base + (long long)tid * SCAN_ITEMS;
+            for (int w = 0; w < SCAN_WARPS; ++w) { unsigned long long v = S.warp_tot[w]; if (w < warp) off += v; agg += v; }
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            long long ck = cprev;
-            if (g0 + k < n) ck = children_upto<MODE>(thread_excl + cum[k], a, nd, inv_n, dRand, pow2, step);
-            cnt[k] = (int)(ck - cprev);
-            if (cnt[k] == 0 && g0 + k < n) zbits |= 1u << k;
-            cprev = ck;
-        }
-        // ---- block scan of zero-slot counts, second look-back
-        int ztot = __popc(zbits);
-        int zinc = ztot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(SMCB_FULL, zinc, o);
-            if (lane >= o) zinc += t;
-        }
-        if (lane == 31) s_warpz[warp] = zinc;
-        __syncthreads();
-        int zwarp_off = 0, ztile = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_WARPS; ++w) { int v = s_warpz[w]; if (w < warp) zwarp_off += v; ztile += v; }
-        if (warp == 0) {
-            unsigned long long ex = lookback_exclusive(a.ws.statusB, tile, (unsigned long long)ztile);
-            if (lane == 0) s_bcast[1] = ex;
-        }
-        __syncthreads();
-        const long long zexcl = (long long)s_bcast[1] + zwarp_off + (zinc - ztot);
-
-        // ---- zero-slot bitmap: 4 threads x 8 slots = one 32-bit word
-        {
-            unsigned m = zbits << (8 * (lane & 3));
-            m |= __shfl_xor_sync(SMCB_FULL, m, 1);
-            m |= __shfl_xor_sync(SMCB_FULL, m, 2);
-            if ((lane & 3) == 0 && g0 < n) {
-                a.am.zmask[g0 >> 5] = m;
-                a.am.zbase[g0 >> 5] = (uint32_t)zexcl;
+            for (int k = 0; k < SCAN_ITEMS; ++k) sq[tid * (SCAN_ITEMS + 1) + k] = off + cum[k];
+            if (tid == 0) {  // publish: tile 0 knows its prefix, everyone else an aggregate
+                volatile unsigned long long* st = a.ws.statusA;
+                st[t1] = (t1 == 0 ? ST_PRE : ST_AGG) | agg;
+                S.bcast[b1] = agg;
             }
         }
-        // ---- surplus list: parent k with count >= 2 owns surplus[E .. E + count - 2]
-        {
-            long long ck1 = cfirst;   // c(k-1)
-            long long zk = zexcl;     // Z[k]
+        __syncthreads();
+
+        // ================= S2: look-back A, children counts, publish zero-slot aggregate =================
+        if (t2 >= 0) {
+            if (warp == 0) {
+                unsigned long long ex = lookback_resolve(a.ws.statusA, t2, S.bcast[b2]);
+                if (lane == 0) S.bcast[b2] = ex;
+            }
+            __syncthreads();
+            const unsigned long long tile_excl = S.bcast[b2];
+            const long long base = (long long)t2 * SCAN_TILE;
+            const long long g0 = base + (long long)tid * SCAN_ITEMS;
+            const unsigned long long* sq = S.cum[b2];
+            int* sc = S.c[b2];
+            const unsigned long long thread_excl = tile_excl + (tid == 0 ? 0ull : sq[(tid - 1) * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]);
+            int cprev = (int)children_upto<MODE>(thread_excl, a, nd, inv_n, dRand, pow2, step);
+            sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS] = cprev;
+            unsigned zbits = 0u;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
-                long long gk = g0 + k;
-                int e = cnt[k] - 1;
-                long long E = ck1 - gk + zk;
-                if (e > 0) {
-                    int small = e < 16 ? e : 16;
-                    for (int r = 0; r < small; ++r) a.am.surplus[E + r] = (uint32_t)gk;
-                }
-                // heavy parents: the warp shares the rest of the writes
-                unsigned hm = __ballot_sync(SMCB_FULL, e > 16);
-                while (hm) {
-                    int src = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    long long hE = __shfl_sync(SMCB_FULL, E, src) + 16;
-                    int he = __shfl_sync(SMCB_FULL, e, src) - 16;
-                    uint32_t hk = (uint32_t)__shfl_sync(SMCB_FULL, gk, src);
-                    if (he > 4096) {  // very heavy: defer to the whole block
-                        if (lane == 0) {
-                            unsigned slot = atomicAdd(&s_heavy_n, 1u);
-                            if (slot < 32) {
-                                s_heavy[3 * slot] = hk; s_heavy[3 * slot + 1] = (unsigned)hE; s_heavy[3 * slot + 2] = (unsigned)he;
-                                he = 0;
-                            }
-                        }
-                        he = __shfl_sync(SMCB_FULL, he, 0);
-                    }
-                    for (int r = lane; r < he; r += 32) a.am.surplus[hE + r] = hk;
-                }
-                ck1 += cnt[k];
-                zk += (zbits >> k) & 1u;
+                int ck = cprev;
+                if (g0 + k < n) ck = (int)children_upto<MODE>(tile_excl + sq[tid * (SCAN_ITEMS + 1) + k], a, nd, inv_n, dRand, pow2, step);
+                if (ck == cprev && g0 + k < n) zbits |= 1u << k;
+                sc[tid * (SCAN_ITEMS + 1) + k] = ck;
+                cprev = ck;
             }
-        }
-        if (a.count_out) {
+            const int ztot = __popc(zbits);
+            int zinc = ztot;
 #pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) if (g0 + k < n) a.count_out[g0 + k] = cnt[k];
-        }
-        __syncthreads();
-        {
-            unsigned hn = s_heavy_n < 32 ? s_heavy_n : 32;
-            for (unsigned h = 0; h < hn; ++h) {
-                uint32_t hk = s_heavy[3 * h]; long long hE = s_heavy[3 * h + 1]; int he = (int)s_heavy[3 * h + 2];
-                for (int r = tid; r < he; r += SCAN_THREADS) a.am.surplus[hE + r] = hk;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(SMCB_FULL, zinc, o);
+                if (lane >= o) zinc += t;
             }
-        }
-        // ---- last tile: unfilled zero-count slots copy particle 0 (reference: uRSIndices zero-initialised, :845)
-        if (tile == ntiles - 1) {
-            __shared__ long long s_tail[2];
-            if (tid == SCAN_THREADS - 1) { s_tail[0] = cprev; s_tail[1] = zexcl + ztot; }
-            // cprev of the last thread = c(n-1) (tail slots beyond n keep cprev), zero slots = Z total
+            if (lane == 31) S.warp_z[warp] = zinc;
             __syncthreads();
-            long long ctot = s_tail[0], ztotal = s_tail[1];
-            long long etot = ctot - n + ztotal;
-            for (long long m = etot + tid; m < ztotal; m += SCAN_THREADS) a.am.surplus[m] = 0u;
+            int zoff = zinc - ztot, zagg = 0;
+#pragma unroll
+            for (int w = 0; w < SCAN_WARPS; ++w) { int v = S.warp_z[w]; if (w < warp) zoff += v; zagg += v; }
+            S.zrel[b2][tid] = zoff;
             if (tid == 0) {
-                if (a.tail_info) { a.tail_info[0] = (unsigned)ctot; a.tail_info[1] = (unsigned)ztotal; }
+                volatile unsigned long long* st = a.ws.statusB;
+                st[t2] = (t2 == 0 ? ST_PRE : ST_AGG) | (unsigned long long)zagg;
+                S.tile[1] = zagg;
             }
         }
         __syncthreads();
+
+        // ================= S3: look-back B, bitmap + surplus lists =================
+        if (t3 >= 0) {
+            if (warp == 0) {
+                unsigned long long ex = lookback_resolve(a.ws.statusB, t3, (unsigned long long)S.tile[2]);
+                if (lane == 0) S.zpre = (long long)ex;
+            }
+            __syncthreads();
+            const long long zprefix = S.zpre;
+            const long long base = (long long)t3 * SCAN_TILE;
+            const long long g0 = base + (long long)tid * SCAN_ITEMS;
+            const int* sc = S.c[b1];
+            const int cfirst = sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS];
+            int cnt[SCAN_ITEMS];
+            unsigned zbits = 0u;
+            {
+                int cp = cfirst;
+#pragma unroll
+                for (int k = 0; k < SCAN_ITEMS; ++k) {
+                    int ck = sc[tid * (SCAN_ITEMS + 1) + k];
+                    cnt[k] = ck - cp;
+                    if (cnt[k] == 0 && g0 + k < n) zbits |= 1u << k;
+                    cp = ck;
+                }
+            }
+            const long long zexcl = zprefix + S.zrel[b1][tid];
+            {   // zero-slot bitmap: 4 threads x 8 slots = one 32-bit word
+                unsigned m = zbits << (8 * (lane & 3));
+                m |= __shfl_xor_sync(SMCB_FULL, m, 1);
+                m |= __shfl_xor_sync(SMCB_FULL, m, 2);
+                if ((lane & 3) == 0 && g0 < n) {
+                    a.am.zmask[g0 >> 5] = m;
+                    a.am.zbase[g0 >> 5] = (uint32_t)zexcl;
+                }
+            }
+            {   // surplus list: parent k with count >= 2 owns surplus[E .. E + count - 2],  E = c(k-1) - k + Z[k]
+                long long ck1 = cfirst, zk = zexcl;
+                unsigned hbits = 0u;
+#pragma unroll
+                for (int k = 0; k < SCAN_ITEMS; ++k) {
+                    long long gk = g0 + k;
+                    write_surplus_small(a.am.surplus, ck1 - gk + zk, cnt[k] - 1, (uint32_t)gk, n);
+                    if (cnt[k] - 1 > SURPLUS_SMALL) hbits |= 1u << k;
+                    ck1 += cnt[k];
+                    zk += (zbits >> k) & 1u;
+                }
+                finish_heavy_runs<SCAN_ITEMS>(a.am.surplus, hbits, cnt, cfirst, zexcl, zbits, g0, n);
+            }
+            if (a.count_out) {
+#pragma unroll
+                for (int k = 0; k < SCAN_ITEMS; ++k) if (g0 + k < n) a.count_out[g0 + k] = cnt[k];
+            }
+            if (t3 == ntiles - 1) {  // unfilled zero-count slots copy particle 0 (reference: uRSIndices zero-initialised, :845)
+                __shared__ long long s_tail[2];
+                if (tid == SCAN_THREADS - 1) { s_tail[0] = sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]; s_tail[1] = zexcl + __popc(zbits); }
+                __syncthreads();
+                long long ctot = s_tail[0], ztotal = s_tail[1];
+                long long etot = ctot - n + ztotal;
+                for (long long m = etot + tid; m < ztotal; m += SCAN_THREADS) a.am.surplus[m] = 0u;
+                if (tid == 0 && a.tail_info) { a.tail_info[0] = (unsigned)ctot; a.tail_info[1] = (unsigned)ztotal; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.tile[2] = S.tile[1];   // zero-slot aggregate of the tile moving from S2 to S3
+        t3 = t2;
+        t2 = t1;
     }
+}
+
+// Host-side launch helpers: the pipelined kernel needs > 48 KB of dynamic shared memory (opt-in attribute).
+template <int SRC, int MODE>
+inline int resample_scan_grid(long long n) {
+    static bool configured = false;
+    if (!configured) {
+        SMCB_CUDA(cudaFuncSetAttribute(k_resample_scan<SRC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+        configured = true;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    SMCB_CUDA(cudaGetDevice(&dev));
+    SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_scan<SRC, MODE>, SCAN_THREADS, SCAN_SMEM_BYTES));
+    if (per_sm < 1) per_sm = 1;
+    long long need = (n + SCAN_TILE - 1) / SCAN_TILE, g = (long long)sms * per_sm;
+    if (g > need) g = need;
+    return (int)(g < 1 ? 1 : g);
+}
+template <int SRC, int MODE>
+inline void launch_resample_scan(const ScanArgs& a, cudaStream_t stream) {
+    int grid = resample_scan_grid<SRC, MODE>(a.n);
+    k_resample_scan<SRC, MODE><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, stream>>>(a);
+    SMCB_CUDA(cudaGetLastError());
 }
 
 // ---- counts -> ancestor map (injected counts, multinomial / residual paths) -----------------------------
@@ -403,24 +610,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
             m |= __shfl_xor_sync(SMCB_FULL, m, 2);
             if ((lane & 3) == 0 && g0 < n) { a.am.zmask[g0 >> 5] = m; a.am.zbase[g0 >> 5] = (uint32_t)zk; }
         }
+        {
+            // E[k] in the closed form used by finish_heavy_runs: E = C - k + Z with C = sum of counts before k; here the
+            // counts may contain zeros that are NOT reflected in a cumulative-children value, so track E directly.
+            long long Ek = E;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            long long gk = g0 + k;
-            int e = cnt[k] - 1;
-            if (e > 0) {
-                int small = e < 16 ? e : 16;
-                for (int r = 0; r < small; ++r) if (E + r < n) a.am.surplus[E + r] = (uint32_t)gk;
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                int e = cnt[k] - 1;
+                if (e > 0) {
+                    for (int r = 0; r < e; ++r) if (Ek + r < n) a.am.surplus[Ek + r] = (uint32_t)(g0 + k);
+                    Ek += e;
+                }
             }
-            unsigned hm = __ballot_sync(SMCB_FULL, e > 16);
-            while (hm) {
-                int src = __ffs(hm) - 1;
-                hm &= hm - 1;
-                long long hE = __shfl_sync(SMCB_FULL, E, src) + 16;
-                int he = __shfl_sync(SMCB_FULL, e, src) - 16;
-                uint32_t hk = (uint32_t)__shfl_sync(SMCB_FULL, gk, src);
-                for (int r = lane; r < he; r += 32) if (hE + r < n) a.am.surplus[hE + r] = hk;
-            }
-            if (e > 0) E += e;
+            E = Ek;
         }
         if (tile == ntiles - 1) {
             __shared__ long long s_tail;
