@@ -44,6 +44,10 @@ int smcb200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * Runs on the device. */
 int smcb200_philox_normals(uint64_t seed, uint32_t stream, uint32_t step, long n, double* out_host);
 
+/* The engine's own device implementations of the elementary functions it uses in place of libm's
+ * (fn: 0 exp(x) for x <= 0, 1 -2 ln(u) for u in (0,1], 2 sin(2 pi u), 3 cos(2 pi u), 4 sqrt(x)); accuracy test surface. */
+int smcb200_fastmath_eval(int fn, const double* in_host, long n, double* out_host);
+
 /* Replaces smc::stableLogSumWeights (population.h:46-50) and sampler::GetESS (sampler.h:413-417).
  * out3 = { log sum exp(logw), ESS = (sum w)^2 / sum w^2, max(logw) }. */
 int smcb200_lse(const double* logw_host, long n, double* out3_host);

@@ -42,6 +42,7 @@ def lib():
     L.smcb200_philox4x32.argtypes = [_c_u32_p, _c_u32_p, _c_u32_p]
     L.smcb200_philox_normals.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_long, _c_double_p]
     L.smcb200_lse.argtypes = [_c_double_p, ctypes.c_long, _c_double_p]
+    L.smcb200_fastmath_eval.argtypes = [ctypes.c_int, _c_double_p, ctypes.c_long, _c_double_p]
     L.smcb200_resample.argtypes = [ctypes.c_int, _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, _c_int_p,
                                    _c_uint_p, _c_int_p]
     L.smcb200_pfNonlinBS.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double,
@@ -94,6 +95,13 @@ def philox4x32(ctr, key):
 def philox_normals(seed, stream, step, n):
     out = np.empty(n, dtype=np.float64)
     _check(lib().smcb200_philox_normals(seed, stream, step, n, _dp(out)))
+    return out
+
+
+def fastmath_eval(fn, x):
+    x = _f64(x)
+    out = np.empty_like(x)
+    _check(lib().smcb200_fastmath_eval(fn, _dp(x), x.size, _dp(out)))
     return out
 
 

@@ -91,6 +91,19 @@ __global__ void k_philox_normals(unsigned long long seed, uint32_t stream, uint3
     if (2 * p + 1 < n) out[2 * p + 1] = z1;
 }
 
+__global__ void k_fastmath(int fn, const double* in, long long n, double* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = in[i], s, c;
+    switch (fn) {
+        case 0: out[i] = fm_exp(x); break;
+        case 1: out[i] = fm_neg2log(x); break;
+        case 2: fm_sincos2pi(x, s, c); out[i] = s; break;
+        case 3: fm_sincos2pi(x, s, c); out[i] = c; break;
+        default: out[i] = fm_sqrt(x); break;
+    }
+}
+
 }  // namespace
 
 // ---- pfNonlinBS handle --------------------------------------------------------------------------------
@@ -137,6 +150,19 @@ int smcb200_philox_normals(uint64_t seed, uint32_t stream, uint32_t step, long n
         k_philox_normals<<<(unsigned)((pairs + 255) / 256), 256>>>(seed, stream, step, n, d.as<double>());
         SMCB_CUDA(cudaGetLastError());
         SMCB_CUDA(cudaMemcpy(out_host, d.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        return SMCB200_OK;
+    });
+}
+
+int smcb200_fastmath_eval(int fn, const double* in_host, long n, double* out_host) {
+    return guarded([&]() -> int {
+        if (n < 1 || !in_host || !out_host || fn < 0 || fn > 4) throw std::invalid_argument("smcb200_fastmath_eval: bad argument");
+        require_device();
+        DevBuf in(sizeof(double) * n), out(sizeof(double) * n);
+        SMCB_CUDA(cudaMemcpy(in.p, in_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+        k_fastmath<<<(unsigned)((n + 255) / 256), 256>>>(fn, in.as<double>(), n, out.as<double>());
+        SMCB_CUDA(cudaGetLastError());
+        SMCB_CUDA(cudaMemcpy(out_host, out.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
         return SMCB200_OK;
     });
 }

@@ -6,6 +6,8 @@
 #include <stdexcept>
 #include <string>
 
+#include "fastmath.cuh"
+
 namespace smcb {
 
 #define SMCB_FULL 0xffffffffu
@@ -53,27 +55,24 @@ struct LseAcc {
 #pragma unroll
         for (int j = 0; j < G; ++j) g[j] = 0.0;
     }
-    // add one element: exactly one exp
+    // add one element: exactly one exp, straight-line (selects, no branches) so that a thread's particles interleave
     __device__ __forceinline__ void add(double lw, const double* h) {
-        if (lw == -INFINITY && m == -INFINITY) return;  // weightless particle, nothing to rescale
-        double d = lw - m;
-        double e = exp(-fabs(d));
-        if (d <= 0.0) {
-            s += e; q = fma(e, e, q);
+        const double d = lw - m;            // +inf for the first finite element, NaN when both are -inf
+        const bool up = d > 0.0;            // lw becomes the new running maximum
+        double e = fm_exp(-fabs(d));
+        e = (lw == -INFINITY) ? 0.0 : e;    // weightless particle contributes nothing (also covers the NaN case)
+        const double e2 = e * e;
+        s = up ? fma(s, e, 1.0) : s + e;
+        q = up ? fma(q, e2, 1.0) : q + e2;
 #pragma unroll
-            for (int j = 0; j < G; ++j) g[j] = fma(e, h[j], g[j]);
-        } else {
-            s = fma(s, e, 1.0); q = fma(q, e * e, 1.0);
-#pragma unroll
-            for (int j = 0; j < G; ++j) g[j] = fma(g[j], e, h[j]);
-            m = lw;
-        }
+        for (int j = 0; j < G; ++j) g[j] = up ? fma(g[j], e, h[j]) : fma(e, h[j], g[j]);
+        m = up ? lw : m;
     }
     __device__ __forceinline__ void merge(const LseAcc& o) {
         if (o.m == -INFINITY) return;
         if (m == -INFINITY) { *this = o; return; }
         double M = fmax(m, o.m);
-        double ea = exp(m - M), eb = exp(o.m - M);
+        double ea = fm_exp(m - M), eb = fm_exp(o.m - M);
         s = s * ea + o.s * eb;
         q = q * (ea * ea) + o.q * (eb * eb);
 #pragma unroll

@@ -24,6 +24,12 @@ namespace smcb {
 
 constexpr int MAX_OBS = 8;
 constexpr int MAX_SHIFT = 4;
+#ifndef SMCB_MASK_LOAD
+#define SMCB_MASK_LOAD 0
+#endif
+#ifndef SMCB_STEP_MINB
+#define SMCB_STEP_MINB 3
+#endif
 constexpr int STEP_THREADS = 256;
 
 // Device control block: every per-step scalar of the reference sampler lives here so that a whole filter
@@ -69,12 +75,13 @@ struct StepArgs {
     const double* znoise;       // injected standard normals in the reference's consumption order, or null
     const double* ures;         // injected resampling base uniforms, one per step, or null
     long long tcap;
+    int dbg;                    // experiment switches (0 in production): 1 identity ancestors, 2 no stores, 4 no RNG, 8 no LSE
 };
 
 enum { PHASE_INIT = 0, PHASE_MOVE = 1, PHASE_OBSERVE = 2 };
 
 template <class Model, int PHASE, bool INJECT>
-__global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
+__global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
     constexpr int D = Model::D, G = Model::NSHIFT, NOBS = Model::NOBS;
     constexpr int NZ = PHASE == PHASE_INIT ? Model::NZ_INIT : Model::NZ_MOVE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,16 +123,24 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
     uint32_t ancB[2] = {0u, 0u};               // stage B result
     double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result
     auto stageA = [&](long long p) {
-        if (PHASE != PHASE_INIT && resampled && p < npairs) {
+        if (PHASE != PHASE_INIT && resampled && p < npairs && !(a.dbg & 1)) {
+#if SMCB_MASK_LOAD == 1
+            mA = __ldcg(a.am.zmask + (p >> 4));
+            bA = __ldcg(a.am.zbase + (p >> 4));
+#elif SMCB_MASK_LOAD == 2
+            mA = a.am.zmask[p >> 4];
+            bA = a.am.zbase[p >> 4];
+#else
             mA = __ldg(a.am.zmask + (p >> 4));
             bA = __ldg(a.am.zbase + (p >> 4));
+#endif
         }
     };
     auto stageB = [&](long long p) {   // consumes mA/bA (loaded for this p one iteration ago)
         if (PHASE != PHASE_INIT && p < npairs) {
             const long long s0 = 2 * p;
             ancB[0] = (uint32_t)s0; ancB[1] = (uint32_t)(s0 + 1);
-            if (resampled) {
+            if (resampled && !(a.dbg & 1)) {
                 const uint32_t bit = (uint32_t)s0 & 31u;
                 const uint32_t below = mA & ((1u << bit) - 1u);
                 const uint32_t rank = bA + __popc(below);
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
                     if (h == 1 && !has1) break;
                     double f[NOBS > 0 ? NOBS : 1];
                     Model::observe(x[h], shift, f);
-                    double w = resampled ? 1.0 : exp(lwv[h]);
+                    double w = resampled ? 1.0 : fm_exp(lwv[h]);
                     obs0 += w;
 #pragma unroll
                     for (int j = 0; j < NOBS; ++j) obs[j] = fma(w, f[j], obs[j]);
@@ -192,8 +207,10 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < NZ; ++k)
-                    philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur, (uint64_t)p, k, z[0][k], z[1][k]);
+                for (int k = 0; k < NZ; ++k) {
+                    if (a.dbg & 4) { z[0][k] = 0.3 + 1e-9 * (double)p; z[1][k] = -0.2; }
+                    else philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur, (uint64_t)p, k, z[0][k], z[1][k]);
+                }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -207,12 +224,14 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(StepArgs<Model> a) {
                     lw = lwv[h];
                     Model::move(tcur, x[h], lw, a.params, z[h]);  // moveset.h:162-168
                 }
+                if (!(a.dbg & 2)) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) dst[d][s] = x[h][d];
-                a.lw[s] = lw;
+                    for (int d = 0; d < D; ++d) dst[d][s] = x[h][d];
+                    a.lw[s] = lw;
+                }
                 double hs[G > 0 ? G : 1];
                 Model::shift_stat(x[h], hs);
-                acc.add(lw, hs);
+                if (a.dbg & 8) { acc.s += lw; acc.m = 0.0; acc.q = 1.0; } else acc.add(lw, hs);
             }
         }
     }
@@ -459,6 +478,7 @@ private:
         a.lw = lw_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
         a.status = status_; a.nstatus = 3 * ntiles_; a.params = params_; a.seed = seed_;
         a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_;
+        { const char* e = getenv("SMCB200_DBGS"); a.dbg = e ? atoi(e) : 0; }
         return a;
     }
     void enqueue_resample() {

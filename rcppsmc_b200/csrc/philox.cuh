@@ -7,6 +7,9 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#ifdef __CUDACC__
+#include "fastmath.cuh"
+#endif
 
 namespace smcb {
 
@@ -74,9 +77,9 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t stream, uint32_t s
     Draw128 d = philox_draw(seed, stream, step, pair_id, slot);
     double u1 = u64_to_open01(d.a);
     double u2 = u64_to_unit(d.b);
-    double r = sqrt(-2.0 * log(u1));
+    double r = fm_sqrt(fm_neg2log(u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    fm_sincos2pi(u2, s, c);
     z0 = r * c;
     z1 = r * s;
 }

@@ -331,6 +331,7 @@ constexpr size_t SCAN_SMEM_BYTES = sizeof(ScanSmem);
 template <int SRC, int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(ScanArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
+    if (a.dbg & 16) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
 
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
                 long long gi = base + i;
                 unsigned long long q = 0ull;
                 if (gi < n) {
-                    double w = (SRC == SRC_LOGW) ? exp(a.in[gi] - lse) : a.in[gi];
+                    double w = (SRC == SRC_LOGW) ? fm_exp(a.in[gi] - lse) : a.in[gi];
                     q = (unsigned long long)__double2ll_rn(w * TWO52);
                 }
                 sq[i + (i >> 3)] = q;

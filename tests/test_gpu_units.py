@@ -132,3 +132,29 @@ def test_invalid_arguments(smc):
         smc.resample(smc.STRATIFIED, np.ones(4) / 4, uniforms=[0.1, 0.2])
     with pytest.raises(smc.SmcError):
         smc.resample(smc.MULTINOMIAL, counts=[3, 3, 0, 0])
+
+
+def _ulp_err(got, exp):
+    return np.abs(got - exp) / np.spacing(np.abs(exp))
+
+
+def test_fastmath_accuracy(smc):
+    # the engine's branch-free elementary functions against numpy (glibc), in units in the last place
+    rng = np.random.default_rng(12)
+    x = np.concatenate([-rng.random(200000) * 50.0, -rng.random(100000) * 700.0, [0.0, -1e-300, -708.0, -709.5, -800.0, -np.inf]])
+    got = smc.fastmath_eval(0, x)
+    exp = np.exp(x)
+    ok = x >= -708.0
+    assert _ulp_err(got[ok], exp[ok]).max() <= 2.0
+    assert np.all(got[~ok] == 0.0)
+    u = np.concatenate([rng.random(300000), 2.0 ** -rng.integers(1, 53, 1000), [1.0, 0.5, 2.0 ** -53, 1.0 - 2.0 ** -53]])
+    u = u[u > 0]
+    got = smc.fastmath_eval(1, u)
+    exp = -2.0 * np.log(u)
+    assert np.all(np.abs(got - exp) <= 4.0 * np.spacing(np.maximum(np.abs(exp), 1e-300)) + 1e-300)
+    v = np.concatenate([rng.random(300000), [0.0, 0.25, 0.5, 0.75, 0.125, 1.0 - 2.0 ** -53]])
+    s, c = smc.fastmath_eval(2, v), smc.fastmath_eval(3, v)
+    assert np.abs(s - np.sin(2 * np.pi * v)).max() <= 1e-15 and np.abs(c - np.cos(2 * np.pi * v)).max() <= 1e-15
+    assert np.abs(s * s + c * c - 1.0).max() <= 1e-15
+    y = np.concatenate([rng.random(200000) * 80.0, 10.0 ** rng.uniform(-16, 2, 100000)])
+    assert _ulp_err(smc.fastmath_eval(4, y), np.sqrt(y)).max() <= 1.0
