@@ -72,7 +72,7 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
  *   noise     optional N*T injected standard normals in the reference's consumption order
  *             (N for Initialise, then N per Iterate), else NULL -> Philox
  *   uniforms  optional injected resampling uniforms, indexed by step: SYSTEMATIC uniforms[t];
- *             STRATIFIED uniforms[t*(N+1) + j]; else NULL -> Philox
+ *             STRATIFIED uniforms[t*(N+1) + j]; MULTINOMIAL / RESIDUAL uniforms[t*N + j]; else NULL -> Philox
  * Outputs (length T each; any may be NULL): mean, sd as returned by pfNonlinBS_impl (:77-78); lognc =
  * GetLogNCPath() after each step; ess = the ESS each step's resampling decision saw; resampled flags. */
 int smcb200_pfNonlinBS(const double* data_host, long T, long particles, int resample_mode, double threshold,

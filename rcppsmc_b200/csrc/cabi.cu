@@ -209,7 +209,7 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
             }
             if (tot > n) throw std::invalid_argument("smcb200_resample: counts sum to more than n");
             SMCB_CUDA(cudaMemcpy(counts.p, counts_in_host, sizeof(int) * n, cudaMemcpyHostToDevice));
-            CountMapArgs a{counts.as<int>(), n, ticket, ws, am, tail};
+            CountMapArgs a{counts.as<int>(), n, nullptr, ticket, ws, am, tail};
             int grid = persistent_grid(k_count_map, SCAN_THREADS, n, SCAN_TILE);
             k_count_map<<<grid, SCAN_THREADS>>>(a);
             SMCB_CUDA(cudaGetLastError());
@@ -232,7 +232,14 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
                 a.ustrat = us.as<double>();
                 launch_resample_scan<SRC_WEIGHTS, STRATIFIED>(a, 0);
             } else {
-                throw std::invalid_argument("smcb200_resample: MULTINOMIAL / RESIDUAL need counts_in in this build");
+                if (!uniforms_host || n_uniforms < n) throw std::invalid_argument("smcb200_resample: MULTINOMIAL / RESIDUAL need n uniforms");
+                us = DevBuf(sizeof(double) * n);
+                SMCB_CUDA(cudaMemcpy(us.p, uniforms_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+                DevBuf cum(sizeof(unsigned long long) * n), extra(sizeof(unsigned long long) * 2);
+                SMCB_CUDA(cudaMemset(extra.p, 0, sizeof(unsigned long long) * 2));
+                DrawWs dw{cum.as<unsigned long long>(), counts.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1)};
+                launch_resample_draws<SRC_WEIGHTS>(mode, w.as<double>(), n, nullptr, nullptr, us.as<double>(), nullptr, 0, ticket, ws, dw, am, tail, 0);
+                SMCB_CUDA(cudaDeviceSynchronize());
             }
             SMCB_CUDA(cudaGetLastError());
         }
@@ -300,8 +307,7 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
     return guarded([&]() -> int {
         if (!h) throw std::invalid_argument("smcb200_pfNonlinBS_run: null handle");
         if (h->T < 1) throw std::runtime_error("smcb200_pfNonlinBS_run: set_data first");
-        if (resample_mode != SMCB200_SYSTEMATIC && resample_mode != SMCB200_STRATIFIED)
-            throw std::invalid_argument("smcb200_pfNonlinBS_run: only SYSTEMATIC and STRATIFIED are built in this revision");
+        if (resample_mode < 0 || resample_mode > 3) throw std::invalid_argument("smcb200_pfNonlinBS_run: unknown resampling mode");
         Sampler<NonlinBS>& s = *h->s;
         NonlinBS::Params p{h->y.as<double>(), h->cterm.as<double>()};
         s.SetParams(p);
@@ -310,7 +316,8 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
         const double* un = h->has_unif ? h->unif.as<double>() : nullptr;
         s.SetInjectedNoise(h->has_noise ? h->noise.as<double>() : nullptr,
                            resample_mode == SMCB200_SYSTEMATIC ? un : nullptr,
-                           resample_mode == SMCB200_STRATIFIED ? un : nullptr);
+                           resample_mode == SMCB200_STRATIFIED ? un : nullptr,
+                           (resample_mode == SMCB200_MULTINOMIAL || resample_mode == SMCB200_RESIDUAL) ? un : nullptr);
         h->mode = resample_mode;
         h->kev_used = 0;
         if (h->profile) {
@@ -326,7 +333,7 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
         for (long t = 1; t < h->T; ++t) s.Iterate();
         s.ObserveFinal();
         SMCB_CUDA(cudaEventRecord(h->ev1, h->stream));
-        h->launches = 2 * h->T + 1;
+        h->launches = h->T * ((resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 2 : 4) + 1;
         h->ran = true;
         return SMCB200_OK;
     });
@@ -394,6 +401,7 @@ int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launc
     return guarded([&]() -> int {
         if (!h || !move_ms || !move_launches || !scan_ms || !scan_launches) throw std::invalid_argument("null argument");
         if (!h->ran || !h->profile || h->kev_used < 3) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: run with profiling enabled first");
+        if (h->mode != SMCB200_SYSTEMATIC && h->mode != SMCB200_STRATIFIED) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: per-kernel split is defined for SYSTEMATIC / STRATIFIED runs");
         SMCB_CUDA(cudaEventSynchronize(h->kev[h->kev_used - 1]));
         // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1
         double mv = 0, sc = 0; long nm = 0, ns = 0;
@@ -428,7 +436,7 @@ int smcb200_pfNonlinBS(const double* data_host, long T, long particles, int resa
     if (!cache) { rc = smcb200_pfNonlinBS_create(particles, T, seed, nullptr, &cache); if (rc) return rc; }
     cache->seed = seed;
     if ((rc = smcb200_pfNonlinBS_set_data(cache, data_host, T))) return rc;
-    long nu = resample_mode == SMCB200_STRATIFIED ? T * (particles + 1) : T;
+    long nu = resample_mode == SMCB200_STRATIFIED ? T * (particles + 1) : (resample_mode == SMCB200_SYSTEMATIC ? T : T * particles);
     if ((rc = smcb200_pfNonlinBS_set_noise(cache, noise_host, uniforms_host, nu))) return rc;
     if ((rc = smcb200_pfNonlinBS_run(cache, resample_mode, threshold))) return rc;
     return smcb200_pfNonlinBS_read(cache, mean_host, sd_host, lognc_host, ess_host, resampled_host);

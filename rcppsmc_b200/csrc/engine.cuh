@@ -47,8 +47,9 @@ struct Ctrl {
     int parity;             // which state buffer holds the current population
     unsigned int done;      // last-block-done counter
     unsigned int ticket;    // scan tile ticket
+    unsigned int ticket2;   // second ticket (count-map kernel of the MULTINOMIAL / RESIDUAL path)
     int n_accepted;
-    int pad;
+    unsigned long long floor_total;  // RESIDUAL: deterministic children handed out this step
 };
 
 struct Traces {             // device arrays of length Tcap
@@ -330,6 +331,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 if (tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
             }
             c->ticket = 0u;
+            c->ticket2 = 0u;
+            c->floor_total = 0ull;
             c->done = 0u;
         }
     }
@@ -389,7 +392,9 @@ public:
     void SetParams(const typename Model::Params& p) { params_ = p; }
     void SetSeed(unsigned long long seed) { seed_ = seed; }
     // Injected randomness (parity testing): device pointers, reference consumption order.
-    void SetInjectedNoise(const double* znoise, const double* ures, const double* ustrat) { znoise_ = znoise; ures_ = ures; ustrat_ = ustrat; }
+    void SetInjectedNoise(const double* znoise, const double* ures, const double* ustrat, const double* udraw = nullptr) {
+        znoise_ = znoise; ures_ = ures; ustrat_ = ustrat; udraw_ = udraw;
+    }
 
     // sampler.h:481-550 (up to and including the resampling decision; the resampling pass itself is enqueued here too)
     void Initialise() {
@@ -491,7 +496,15 @@ private:
         switch (mode_) {
             case SYSTEMATIC: launch_resample_scan<SRC_LOGW, SYSTEMATIC>(s, stream_); break;
             case STRATIFIED: launch_resample_scan<SRC_LOGW, STRATIFIED>(s, stream_); break;
-            default: throw std::invalid_argument("resampling mode not available in the fused engine yet");
+            case MULTINOMIAL:
+            case RESIDUAL: {
+                if (!cum_) { cum_ = dalloc<unsigned long long>(n_); count_ = dalloc<int>(n_); }
+                DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2};
+                launch_resample_draws<SRC_LOGW>(mode_, lw_, n_, &ctrl_->lse, &ctrl_->resampled, udraw_, &ctrl_->T, seed_,
+                                                &ctrl_->ticket, s.ws, dw, am_, nullptr, stream_);
+                break;
+            }
+            default: throw std::invalid_argument("unknown resampling mode");
         }
         SMCB_CUDA(cudaGetLastError());
         if (after_launch_) after_launch_();
@@ -514,6 +527,9 @@ private:
     const double* znoise_ = nullptr;
     const double* ures_ = nullptr;
     const double* ustrat_ = nullptr;
+    const double* udraw_ = nullptr;   // MULTINOMIAL / RESIDUAL injected uniforms U[step][n]
+    unsigned long long* cum_ = nullptr;
+    int* count_ = nullptr;
     int grid_init_ = 1, grid_move_ = 1, grid_scan_ = 1;
     long long steps_ = 0;
     std::function<void()> after_launch_;

@@ -541,6 +541,7 @@ inline void launch_resample_scan(const ScanArgs& a, cudaStream_t stream) {
 struct CountMapArgs {
     const int* count;
     long long n;
+    const int* enable_ptr;
     unsigned int* ticket;
     ScanWs ws;
     AncestorMap am;
@@ -548,6 +549,7 @@ struct CountMapArgs {
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
     __shared__ int s_c[SCAN_TILE + SCAN_TILE / 8];
     __shared__ unsigned long long s_ws[SCAN_WARPS];
     __shared__ int s_wz[SCAN_WARPS];
@@ -637,6 +639,185 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
         }
         __syncthreads();
     }
+}
+
+// ---- MULTINOMIAL / RESIDUAL: the engine's native definitions (the reference delegates to R's rmultinom,
+// sampler.h:790,801, which is absent and inherently sequential; see DESIGN.md and oracle/smc_oracle.c) --------------
+//   q_i = rint(w_i 2^52);  MULTINOMIAL scans q; RESIDUAL takes floor_i = floor(n q_i / 2^52) deterministic children
+//   and scans the (right-shifted) 52-bit fractions.  Draw j: m_j = floor(U_j 2^53), t_j = floor(m_j Q / 2^53),
+//   ancestor = min{k : C_k > t_j} over the inclusive integer scan C (Q = C_{n-1}).  All integer, all exact.
+struct CumArgs {
+    const double* in;            // SRC_LOGW: log-weights; SRC_WEIGHTS: normalised weights
+    long long n;
+    const double* lse_ptr;
+    const int* enable_ptr;
+    unsigned int* ticket;
+    unsigned long long* status;  // [ntiles]
+    unsigned long long* cum;     // [n] out: inclusive scan
+    int* count;                  // [n] out: zeros (MULTINOMIAL) or floor counts (RESIDUAL)
+    unsigned long long* floor_total;  // RESIDUAL: sum of floor counts (device scalar, zeroed by the caller)
+    int shift;                   // RESIDUAL: right shift applied to the 52-bit fractions
+};
+
+template <int SRC, bool RESID>
+__global__ void __launch_bounds__(SCAN_THREADS) k_cum_scan(CumArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    __shared__ unsigned long long s_q[SCAN_PAD];
+    __shared__ unsigned long long s_warp[SCAN_WARPS];
+    __shared__ unsigned long long s_bcast;
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n = a.n;
+    const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
+    unsigned long long fsum = 0ull;
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const long long base = (long long)tile * SCAN_TILE;
+#pragma unroll
+        for (int r = 0; r < SCAN_ITEMS; ++r) {
+            int i = r * SCAN_THREADS + tid;
+            long long gi = base + i;
+            unsigned long long v = 0ull;
+            if (gi < n) {
+                double w = (SRC == SRC_LOGW) ? fm_exp(a.in[gi] - lse) : a.in[gi];
+                unsigned long long q = (unsigned long long)__double2ll_rn(w * TWO52);
+                if (RESID) {
+                    unsigned long long hi = __umul64hi(q, (unsigned long long)n), lo = q * (unsigned long long)n;
+                    unsigned long long fl = (hi << 12) | (lo >> 52);           // floor(n q / 2^52)
+                    unsigned long long fr = lo & ((1ull << 52) - 1ull);         // 52-bit fraction
+                    a.count[gi] = (int)fl;
+                    fsum += fl;
+                    v = fr >> a.shift;
+                } else {
+                    a.count[gi] = 0;
+                    v = q;
+                }
+            }
+            s_q[i + (i >> 3)] = v;
+        }
+        __syncthreads();
+        unsigned long long cum[SCAN_ITEMS];
+        {
+            unsigned long long run = 0ull;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) { run += s_q[tid * (SCAN_ITEMS + 1) + k]; cum[k] = run; }
+        }
+        const unsigned long long tot = cum[SCAN_ITEMS - 1];
+        unsigned long long inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(SMCB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long off = inc - tot, agg = 0ull;
+#pragma unroll
+        for (int w = 0; w < SCAN_WARPS; ++w) { unsigned long long v = s_warp[w]; if (w < warp) off += v; agg += v; }
+        if (warp == 0) {
+            unsigned long long ex = lookback_exclusive(a.status, tile, agg);
+            if (lane == 0) s_bcast = ex;
+        }
+        __syncthreads();
+        const unsigned long long excl = s_bcast + off;
+        const long long g0 = base + (long long)tid * SCAN_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) if (g0 + k < n) a.cum[g0 + k] = excl + cum[k];
+        __syncthreads();
+    }
+    if (RESID) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(SMCB_FULL, fsum, o);
+        if (lane == 0 && fsum) atomicAdd(a.floor_total, fsum);
+    }
+}
+
+struct DrawArgs {
+    const unsigned long long* cum;   // [n] inclusive integer scan
+    long long n;
+    const int* enable_ptr;
+    const unsigned long long* floor_total;  // RESIDUAL: draws = n - *floor_total; null -> n draws
+    const double* uniforms;          // injected U[step][0..n), or null -> Philox(seed, step)
+    const long long* step_ptr;
+    unsigned long long seed;
+    int* count;                      // [n] in/out: += children per parent
+};
+
+__global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const long long n = a.n;
+    const long long ndraws = a.floor_total ? n - (long long)*a.floor_total : n;
+    const long long step = a.step_ptr ? *a.step_ptr : 0;
+    const unsigned long long Q = a.cum[n - 1];
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ndraws; j += (long long)gridDim.x * blockDim.x) {
+        unsigned long long m;
+        if (a.uniforms) m = (unsigned long long)(a.uniforms[step * n + j] * 9007199254740992.0);
+        else m = philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 2).a >> 11;
+        // t = floor(m Q / 2^53)
+        unsigned long long hi = __umul64hi(m, Q), lo = m * Q;
+        unsigned long long t = (hi << 11) | (lo >> 53);
+        long long l = 0, h = n - 1;  // min k with cum[k] > t
+        while (l < h) {
+            long long mid = (l + h) >> 1;
+            if (__ldg(a.cum + mid) > t) h = mid; else l = mid + 1;
+        }
+        atomicAdd(a.count + l, 1);
+    }
+}
+
+inline int residual_shift(long long n) {
+    int nb = 0;
+    while ((1LL << nb) < n) ++nb;
+    return nb > 11 ? nb - 11 : 0;
+}
+
+struct DrawWs {                      // extra workspace of the MULTINOMIAL / RESIDUAL path
+    unsigned long long* cum;         // [n]
+    int* count;                      // [n]
+    unsigned long long* floor_total; // device scalar (zero on entry)
+    unsigned int* ticket2;           // second tile ticket (zero on entry)
+};
+
+// weights -> integer scan -> iid draws -> children counts -> ancestor map.  `ticket`, `ticket2`, `floor_total` and the
+// three status arrays must be zero on entry.
+template <int SRC>
+inline void launch_resample_draws(int mode, const double* in, long long n, const double* lse_ptr, const int* enable_ptr,
+                                  const double* uniforms, const long long* step_ptr, unsigned long long seed,
+                                  unsigned int* ticket, const ScanWs& ws, const DrawWs& dw, const AncestorMap& am,
+                                  unsigned int* tail_info, cudaStream_t stream) {
+    static int grid_cum = 0, grid_map = 0, grid_draw = 0;
+    if (!grid_cum) {
+        int dev = 0, sms = 0, b = 0;
+        SMCB_CUDA(cudaGetDevice(&dev));
+        SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_cum_scan<SRC, false>, SCAN_THREADS, 0));
+        grid_cum = sms * (b < 1 ? 1 : b);
+        SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_count_map, SCAN_THREADS, 0));
+        grid_map = sms * (b < 1 ? 1 : b);
+        grid_draw = sms * 8;
+    }
+    const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CumArgs c{};
+    c.in = in; c.n = n; c.lse_ptr = lse_ptr; c.enable_ptr = enable_ptr; c.ticket = ticket; c.status = ws.statusA;
+    c.cum = dw.cum; c.count = dw.count; c.floor_total = dw.floor_total; c.shift = residual_shift(n);
+    int g = (int)(tiles < grid_cum ? tiles : grid_cum);
+    if (mode == RESIDUAL) k_cum_scan<SRC, true><<<g, SCAN_THREADS, 0, stream>>>(c);
+    else k_cum_scan<SRC, false><<<g, SCAN_THREADS, 0, stream>>>(c);
+    SMCB_CUDA(cudaGetLastError());
+    DrawArgs d{};
+    d.cum = dw.cum; d.n = n; d.enable_ptr = enable_ptr; d.floor_total = mode == RESIDUAL ? dw.floor_total : nullptr;
+    d.uniforms = uniforms; d.step_ptr = step_ptr; d.seed = seed; d.count = dw.count;
+    long long need = (n + 255) / 256;
+    k_multinomial_draw<<<(int)(need < grid_draw ? need : grid_draw), 256, 0, stream>>>(d);
+    SMCB_CUDA(cudaGetLastError());
+    CountMapArgs m{dw.count, n, enable_ptr, dw.ticket2, ws, am, tail_info};
+    g = (int)(tiles < grid_map ? tiles : grid_map);
+    k_count_map<<<g, SCAN_THREADS, 0, stream>>>(m);
+    SMCB_CUDA(cudaGetLastError());
 }
 
 // Materialise uRSIndices (sampler.h:845-857 layout) from the ancestor map.

@@ -20,12 +20,12 @@ def _inject_case(N, T, mode, seed):
     rng = np.random.default_rng(seed)
     _, y = H.sim_nonlin(T, seed)
     z = rng.standard_normal(N * T)
-    U = rng.random(T if mode == H.SYSTEMATIC else T * (N + 1))
+    U = rng.random({H.SYSTEMATIC: T, H.STRATIFIED: T * (N + 1)}.get(mode, T * N))
     return y, z, U
 
 
 @pytest.mark.parametrize("N,T", [(1000, 50), (1, 5), (2, 7), (37, 20), (4099, 30), (1 << 15, 12)])
-@pytest.mark.parametrize("mode", [H.SYSTEMATIC, H.STRATIFIED])
+@pytest.mark.parametrize("mode", [H.SYSTEMATIC, H.STRATIFIED, H.MULTINOMIAL, H.RESIDUAL])
 def test_traces_match_oracle_on_identical_draws(smc, N, T, mode):
     y, z, U = _inject_case(N, T, mode, seed=N + T + mode)
     got = smc.pfNonlinBS(y, N, resample_mode=mode, threshold=1.01 * N, noise=z, uniforms=U, full=True)
@@ -77,6 +77,18 @@ def test_philox_runs_agree_with_oracle_within_monte_carlo_error(smc):
     se = np.sqrt(gm.var(axis=0, ddof=1) / R + om.var(axis=0, ddof=1) / R)
     zscore = np.abs(gm.mean(axis=0) - om.mean(axis=0)) / se
     assert (zscore < 3.0).mean() >= 0.95 and zscore.max() < 4.5
+
+
+def test_reference_default_mode_multinomial_statistics(smc):
+    # the drop-in default of pfNonlinBS_impl (MULTINOMIAL, threshold 1.01 N; src/pfnonlinbs.cpp:62) under Philox:
+    # filtering means agree with SYSTEMATIC runs of the oracle within Monte Carlo error
+    N, T, R = 4000, 20, 20
+    _, y = H.sim_nonlin(T, 4)
+    gm = np.array([smc.pfNonlinBS(y, N, seed=300 + r)["mean"] for r in range(R)])   # defaults = reference behaviour
+    om = np.array([H.o_pfnonlinbs(y, N, H.MULTINOMIAL, 1.01 * N, seed=700 + r)["mean"] for r in range(R)])
+    se = np.sqrt(gm.var(axis=0, ddof=1) / R + om.var(axis=0, ddof=1) / R)
+    zscore = np.abs(gm.mean(axis=0) - om.mean(axis=0)) / se
+    assert (zscore < 3.0).mean() >= 0.9 and zscore.max() < 4.5
 
 
 def test_philox_run_is_deterministic_and_seed_sensitive(smc):

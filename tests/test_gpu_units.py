@@ -90,6 +90,21 @@ def test_count_map_bit_exact_vs_oracle(smc, n):
         assert np.array_equal(idx, oidx)
 
 
+@pytest.mark.parametrize("n", [1, 2, 9, 2047, 2049, 30000, 1 << 18])
+@pytest.mark.parametrize("mode", [H.MULTINOMIAL, H.RESIDUAL])
+def test_native_multinomial_residual_bit_exact_vs_oracle(smc, n, mode):
+    # the engine's native definitions (iid uniforms through the exact integer inverse CDF; integer residual split)
+    rng = np.random.default_rng(50 + n + mode)
+    for spread in (0.7, 5.0):
+        w = H.random_weights(rng, n, spread)
+        U = rng.random(n)
+        idx, cnt = smc.resample(mode, w, U, return_counts=True)
+        oidx, ocnt = H.o_resample_w(mode, w, U)
+        assert cnt.sum() == n
+        assert np.array_equal(cnt, ocnt)
+        assert np.array_equal(idx, oidx)
+
+
 def test_resample_degenerate_weights(smc):
     # one particle carries (almost) everything: exercises the heavy-parent paths of the surplus writer
     for n in (5000, 1 << 18):
