@@ -103,6 +103,23 @@ int smcb200_pfNonlinBS_set_profile(smcb200_pf* h, int on);
 int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launches, float* scan_ms, long* scan_launches);
 int smcb200_pfNonlinBS_destroy(smcb200_pf* h);
 
+/* ---- model level: pfLineartBS (reference src/pflineart.cpp:53-99, R/pfLineartBS.R) ------------------- */
+
+/* Per-step callback: the reference calls the R closure fun(Xm, Ym) after every Iterate when usef is TRUE
+ * (src/pflineart.cpp:85); entries beyond the current step are 0.  NULL = usef FALSE. */
+typedef void (*smcb200_step_callback)(const double* Xm, const double* Ym, long T, void* user);
+
+/* `data` is the reference's arma::mat [T x 2] in column-major order (x column, then y column).
+ * Reference behaviour: resample_mode = SMCB200_RESIDUAL, threshold = 0.5 (src/pflineart.cpp:67).
+ * noise: optional 4*N*T injected standard normals in the reference's consumption order (per particle x_pos, y_pos,
+ * x_vel, y_vel at Initialise; x_pos, x_vel, y_pos, y_vel per move, :147-150, :163-166); uniforms as in
+ * smcb200_pfNonlinBS.  Outputs: Xm, Xv, Ym, Yv as returned by pfLineartBS_impl (:90-93; Xv/Yv are variances) plus the
+ * logNC path, ESS and resampled traces. */
+int smcb200_pfLineartBS(const double* data_host, long T, long particles, int resample_mode, double threshold,
+                        uint64_t seed, const double* noise_host, const double* uniforms_host,
+                        smcb200_step_callback callback, void* user, double* Xm_host, double* Xv_host, double* Ym_host,
+                        double* Yv_host, double* lognc_host, double* ess_host, int* resampled_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,11 +27,15 @@ int smco_resample(int mode, const double* logw, long n, const double* U, long nU
                   const int* counts_in, unsigned* idx, int* count_out);
 double smco_integrate(const double* logw, const double* f, long n);
 
+void smco_set_uniforms_by_step(int on);
 void smco_sim_nonlin(long T, const double* z_state, const double* z_obs, double var_init,
                      double var_evol, double var_obs, double cos_offset, double* x, double* y);
 int smco_pfnonlinbs(const double* y, long T, long N, int mode, double threshold, const double* z,
                     const double* U, unsigned long long seed, double* mean, double* sd,
                     double* lognc, double* ess, int* resampled, unsigned* idx_trace);
+int smco_pflineart(const double* data, long T, long N, int mode, double threshold, const double* z, const double* U,
+                   unsigned long long seed, double* Xm, double* Xv, double* Ym, double* Yv, double* lognc, double* ess,
+                   int* resampled);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 

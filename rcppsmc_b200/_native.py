@@ -48,6 +48,9 @@ def lib():
     L.smcb200_pfNonlinBS.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double,
                                      ctypes.c_uint64, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                      _c_double_p, _c_double_p, _c_int_p]
+    L.smcb200_pfLineartBS.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_uint64,
+                                      _c_double_p, _c_double_p, ctypes.c_void_p, ctypes.c_void_p, _c_double_p, _c_double_p,
+                                      _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_set_data.argtypes = [ctypes.c_void_p, _c_double_p, ctypes.c_long]
@@ -144,6 +147,37 @@ def pfNonlinBS(data, particles, resample_mode=MULTINOMIAL, threshold=None, seed=
     _check(lib().smcb200_pfNonlinBS(_dp(y), T, particles, resample_mode, thr, seed, _dp(z), _dp(u), _dp(mean), _dp(sd),
                                     _dp(lognc), _dp(ess), res.ctypes.data_as(_c_int_p)))
     out = {"mean": mean, "sd": sd}
+    if full:
+        out.update(logNC=lognc, ESS=ess, resampled=res)
+    return out
+
+
+_STEP_CB = ctypes.CFUNCTYPE(None, _c_double_p, _c_double_p, ctypes.c_long, ctypes.c_void_p)
+
+
+def pfLineartBS(data, particles, usef=False, fun=None, resample_mode=RESIDUAL, threshold=0.5, seed=1, noise=None,
+                uniforms=None, full=False):
+    """Mirror of ``pfLineartBS_impl(data, part, usef, fun)`` (reference src/pflineart.cpp:53-99): dict(Xm, Xv, Ym, Yv).
+
+    ``data`` is a [T x 2] array (x, y observation columns).  ``fun(Xm, Ym)`` is called after every step when ``usef``.
+    Trailing keyword arguments are the ABI extensions (the reference hard-codes RESIDUAL, 0.5)."""
+    d = np.asfortranarray(np.asarray(data, dtype=np.float64))
+    if d.ndim != 2 or d.shape[1] != 2:
+        raise ValueError("data must be [T x 2]")
+    T = d.shape[0]
+    flat = np.ascontiguousarray(d.T.reshape(-1))  # column-major: x column then y column
+    Xm, Xv, Ym, Yv, lognc, ess = (np.empty(T) for _ in range(6))
+    res = np.empty(T, dtype=np.int32)
+    z, u = _f64(noise), _f64(uniforms)
+    cb = None
+    if usef and fun is not None:
+        def _cb(xm, ym, n, _user):
+            fun(np.ctypeslib.as_array(xm, shape=(n,)).copy(), np.ctypeslib.as_array(ym, shape=(n,)).copy())
+        cb = _STEP_CB(_cb)
+    _check(lib().smcb200_pfLineartBS(_dp(flat), T, particles, resample_mode, threshold, seed, _dp(z), _dp(u),
+                                     ctypes.cast(cb, ctypes.c_void_p) if cb else None, None, _dp(Xm), _dp(Xv), _dp(Ym), _dp(Yv),
+                                     _dp(lognc), _dp(ess), res.ctypes.data_as(_c_int_p)))
+    out = {"Xm": Xm, "Xv": Xv, "Ym": Ym, "Yv": Yv}
     if full:
         out.update(logNC=lognc, ESS=ess, resampled=res)
     return out

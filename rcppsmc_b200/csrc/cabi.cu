@@ -8,49 +8,17 @@
 #include <string>
 #include <vector>
 
-#include "engine.cuh"
+#include "cabi_common.cuh"
 #include "models.cuh"
 
 using namespace smcb;
 
+namespace smcb_abi {
+std::string& last_error() { thread_local std::string e; return e; }
+}  // namespace smcb_abi
+using namespace smcb_abi;
+
 namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-template <class F>
-int guarded(F&& f) {
-    try {
-        return f();
-    } catch (const CudaError& e) {
-        return fail(SMCB200_ERR_CUDA, e.what());
-    } catch (const std::invalid_argument& e) {
-        return fail(SMCB200_ERR_INVALID, e.what());
-    } catch (const std::exception& e) {
-        return fail(SMCB200_ERR_STATE, e.what());
-    }
-}
-
-void require_device() {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n < 1)
-        throw CudaError(std::string("no CUDA device available (this library has no CPU fallback): ") +
-                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-}
-
-struct DevBuf {
-    void* p = nullptr;
-    DevBuf() {}
-    explicit DevBuf(size_t bytes) { SMCB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); }
-    ~DevBuf() { if (p) cudaFree(p); }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (p) cudaFree(p); p = o.p; o.p = nullptr; return *this; }
-    template <class T> T* as() const { return (T*)p; }
-};
 
 // ---- log-sum-exp / ESS reduction (population.h:46-50, sampler.h:413-417) --------------------------------
 __global__ void __launch_bounds__(256) k_lse(const double* lw, long long n, double* partial, unsigned int* done, double* out3) {
@@ -125,7 +93,7 @@ struct smcb200_pf {
 
 extern "C" {
 
-const char* smcb200_last_error(void) { return g_err.c_str(); }
+const char* smcb200_last_error(void) { return last_error().c_str(); }
 int smcb200_version(void) { return 100; }
 int smcb200_device_count(void) {
     int n = 0;

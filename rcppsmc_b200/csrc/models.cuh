@@ -58,4 +58,52 @@ struct NonlinBS {
     }
 };
 
+
+// Constant-velocity tracking with Student-t observation noise: reference src/pflineart.cpp:32-169,
+// inst/include/pflineart.h:28-60.  State (x_pos, y_pos, x_vel, y_vel) in that SoA order.
+struct Lineart {
+    static constexpr int D = 4;
+    static constexpr int NZ_INIT = 4;
+    static constexpr int NZ_MOVE = 4;
+    static constexpr int NSHIFT = 2;
+    static constexpr int NOBS = 4;
+    struct Params {
+        const double* yx;  // observed x positions y.x_pos[0..T)
+        const double* yy;  // observed y positions
+    };
+    static constexpr double scale_y = 0.1, nu_y = 10.0, Delta = 0.1;  // src/pflineart.cpp:38-40
+
+    __device__ static __forceinline__ double loglik(const Params& p, long long t, const double (&x)[D]) {  // :134-137
+        double ax = (x[0] - p.yx[t]) / scale_y;
+        double ay = (x[1] - p.yy[t]) / scale_y;
+        return (-0.5 * (nu_y + 1.0)) * (log(1 + (ax * ax) / nu_y) + log(1 + (ay * ay) / nu_y));
+    }
+    __device__ static __forceinline__ void init(double (&x)[D], double& lw, const Params& p, const double* z) {  // :144-152
+        x[0] = 0.0 + 2.0 * z[0];   // sqrt(var_s0) = 2
+        x[1] = 0.0 + 2.0 * z[1];
+        x[2] = 0.0 + 1.0 * z[2];   // sqrt(var_u0) = 1
+        x[3] = 0.0 + 1.0 * z[3];
+        lw = loglik(p, 0, x);
+    }
+    __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {  // :161-169
+        const double sd_s = 0.1414213562373095;    // sqrt(var_s = 0.02)
+        const double sd_u = 0.03162277660168379;   // sqrt(var_u = 0.001)
+        x[0] += x[2] * Delta + (0.0 + sd_s * z[0]);
+        x[2] += (0.0 + sd_u * z[1]);
+        x[1] += x[3] * Delta + (0.0 + sd_s * z[2]);
+        x[3] += (0.0 + sd_u * z[3]);
+        lw += loglik(p, t, x);
+    }
+    __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[NSHIFT]) { h[0] = x[0]; h[1] = x[1]; }
+    // integrand_mean_x / var_x / mean_y / var_y (:103-128), centred on the pre-resample weighted means
+    __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[NOBS]) {
+        double dx = x[0] - shift[0], dy = x[1] - shift[1];
+        f[0] = dx; f[1] = dx * dx; f[2] = dy; f[3] = dy * dy;
+    }
+    __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {
+        out[0] = shift[0] + v[0]; out[1] = v[1] - v[0] * v[0];   // Xm, Xv (variance, the reference takes no square root: :90-93)
+        out[2] = shift[1] + v[2]; out[3] = v[3] - v[2] * v[2];   // Ym, Yv
+    }
+};
+
 }  // namespace smcb

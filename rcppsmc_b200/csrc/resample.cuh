@@ -263,7 +263,7 @@ __device__ __forceinline__ void write_surplus_small(uint32_t* __restrict__ surpl
         for (int r = 0; r < small; ++r) if (E + r < cap) surplus[E + r] = gk;
     }
 }
-__device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ surplus, long long hE, long long hend, uint32_t hk, long long cap) {
+static __device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ surplus, long long hE, long long hend, uint32_t hk, long long cap) {
     const int lane = threadIdx.x & 31;
     if (hend > cap) hend = cap;
     if (hend - hE >= 1024) {
@@ -548,7 +548,7 @@ struct CountMapArgs {
     unsigned int* tail_info;
 };
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     __shared__ int s_c[SCAN_TILE + SCAN_TILE / 8];
     __shared__ unsigned long long s_ws[SCAN_WARPS];
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs a) {
 }
 
 // ---- MULTINOMIAL / RESIDUAL: the engine's native definitions (the reference delegates to R's rmultinom,
-// sampler.h:790,801, which is absent and inherently sequential; see DESIGN.md and oracle/smc_oracle.c) --------------
+// sampler.h:790,801, which is absent and inherently sequential) ------------------------------------------
 //   q_i = rint(w_i 2^52);  MULTINOMIAL scans q; RESIDUAL takes floor_i = floor(n q_i / 2^52) deterministic children
 //   and scans the (right-shifted) 52-bit fractions.  Draw j: m_j = floor(U_j 2^53), t_j = floor(m_j Q / 2^53),
 //   ancestor = min{k : C_k > t_j} over the inclusive integer scan C (Q = C_{n-1}).  All integer, all exact.
@@ -747,7 +747,7 @@ struct DrawArgs {
     int* count;                      // [n] in/out: += children per parent
 };
 
-__global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
+static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     const long long n = a.n;
     const long long ndraws = a.floor_total ? n - (long long)*a.floor_total : n;
@@ -821,12 +821,12 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
 }
 
 // Materialise uRSIndices (sampler.h:845-857 layout) from the ancestor map.
-__global__ void k_decode_indices(AncestorMap am, long long n, uint32_t* idx) {
+static __global__ void k_decode_indices(AncestorMap am, long long n, uint32_t* idx) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) idx[i] = decode_ancestor(am, i);
 }
 
-__global__ void k_zero_u64(unsigned long long* p, long long n) {
+static __global__ void k_zero_u64(unsigned long long* p, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0ull;
 }

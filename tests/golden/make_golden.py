@@ -87,6 +87,21 @@ def main():
         k += 1
     out["ncases"] = np.array(k)
     np.savez_compressed(os.path.join(HERE, "pfnonlinbs_kat.npz"), **out)
+    # ---- 4. pfLineartBS traces from the reference sampler + pflineart_move on injected draws
+    out = {}
+    k = 0
+    for (N, T, mode, thr) in ((150, 30, H.SYSTEMATIC, 0.5), (150, 30, H.STRATIFIED, 0.5), (40, 10, H.SYSTEMATIC, 41.0)):
+        data = H.sim_lineart(T, 200 + k)
+        z = rng.standard_normal(4 * N * T)
+        U = rng.random(T * (N + 1))
+        r = H.r_pflineart(data, N, mode, thr, z, U)
+        out[f"N{k}"] = np.array(N); out[f"T{k}"] = np.array(T); out[f"mode{k}"] = np.array(mode); out[f"thr{k}"] = np.array(thr)
+        out[f"data{k}"] = data; out[f"z{k}"] = z; out[f"U{k}"] = U
+        for key in ("Xm", "Xv", "Ym", "Yv", "logNC", "ESS", "resampled"):
+            out[f"{key}{k}"] = r[key]
+        k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "pflineart_kat.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

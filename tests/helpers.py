@@ -120,7 +120,8 @@ def sim_nonlin(T, seed, var_init=10.0, var_evol=10.0, var_obs=1.0, cos_offset=-1
     return x, y
 
 
-def o_pfnonlinbs(y, N, mode, threshold, z=None, U=None, seed=0, want_idx=False):
+def o_pfnonlinbs(y, N, mode, threshold, z=None, U=None, seed=0, want_idx=False, by_step=False):
+    oracle().smco_set_uniforms_by_step(1 if by_step else 0)
     y = f64(y)
     T = y.size
     mean, sd, nc, ess = np.empty(T), np.empty(T), np.empty(T), np.empty(T)
@@ -197,3 +198,43 @@ def random_weights(rng, n, spread=3.0, grid=True):
     w = np.exp(lw - lw.max())
     w /= w.sum()
     return o_quantise(w) if grid else w
+
+
+# ---- pfLineartBS ------------------------------------------------------------------------------------------
+def sim_lineart(T, seed):
+    """Restated R/simLineart.R:1-15: two Gaussian random walks observed with Student-t(4) noise.  Returns [T x 2]."""
+    rng = np.random.default_rng(seed)
+    sx, sy = np.cumsum(rng.standard_normal(T)), np.cumsum(rng.standard_normal(T))
+    return np.column_stack([sx + rng.standard_t(4, T), sy + rng.standard_t(4, T)])
+
+
+def _colmajor(data):
+    return np.ascontiguousarray(np.asarray(data, dtype=np.float64).T.reshape(-1))
+
+
+def o_pflineart(data, N, mode, threshold, z=None, U=None, seed=0, by_step=False):
+    oracle().smco_set_uniforms_by_step(1 if by_step else 0)
+    d = _colmajor(data)
+    T = d.size // 2
+    out = {k: np.empty(T) for k in ("Xm", "Xv", "Ym", "Yv", "logNC", "ESS")}
+    rs = np.empty(T, dtype=np.int32)
+    z = None if z is None else f64(z)
+    U = None if U is None else f64(U)
+    rc = oracle().smco_pflineart(dp(d), L(T), L(N), mode, D(threshold), dp(z), dp(U), ctypes.c_ulonglong(seed), dp(out["Xm"]),
+                                 dp(out["Xv"]), dp(out["Ym"]), dp(out["Yv"]), dp(out["logNC"]), dp(out["ESS"]), rs.ctypes.data_as(IP))
+    assert rc == 0
+    out["resampled"] = rs
+    return out
+
+
+def r_pflineart(data, N, mode, threshold, z, U):
+    d = _colmajor(data)
+    T = d.size // 2
+    r_clear()
+    r_push(normals=z, uniforms=U)
+    out = {k: np.empty(T) for k in ("Xm", "Xv", "Ym", "Yv", "logNC", "ESS")}
+    rs = np.empty(T, dtype=np.int32)
+    ref().smcref_pflineart(dp(d), L(T), L(N), mode, D(threshold), dp(out["Xm"]), dp(out["Xv"]), dp(out["Ym"]), dp(out["Yv"]),
+                           dp(out["logNC"]), dp(out["ESS"]), rs.ctypes.data_as(IP))
+    out["resampled"] = rs
+    return out

@@ -43,10 +43,7 @@ def test_ess_triggered_resampling_matches_oracle(smc, thr):
     N, T = 2000, 40
     y, z, U = _inject_case(N, T, H.SYSTEMATIC, seed=5)
     got = smc.pfNonlinBS(y, N, resample_mode=H.SYSTEMATIC, threshold=thr, noise=z, uniforms=U, full=True)
-    # the oracle consumes one uniform per RESAMPLE; the ABI indexes uniforms by step: remap
-    exp0 = H.o_pfnonlinbs(y, N, H.SYSTEMATIC, thr, z=z, U=U)
-    steps = np.flatnonzero(exp0["resampled"])
-    exp = H.o_pfnonlinbs(y, N, H.SYSTEMATIC, thr, z=z, U=U[steps])
+    exp = H.o_pfnonlinbs(y, N, H.SYSTEMATIC, thr, z=z, U=U, by_step=True)  # the ABI indexes injected uniforms by step
     assert 0 < exp["resampled"].sum() < T
     assert np.array_equal(got["resampled"], exp["resampled"])
     np.testing.assert_allclose(got["logNC"], exp["logNC"], rtol=RTOL, atol=1e-9)

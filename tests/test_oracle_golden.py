@@ -80,3 +80,15 @@ def test_native_multinomial_and_residual_definitions():
     assert cnt.sum() == n
     assert np.all(cnt >= np.floor(n * w - 1e-9).astype(int))
     assert np.all(cnt <= np.floor(n * w).astype(int) + (n - np.floor(n * w).sum()))
+
+
+def test_pflineart_traces_bit_exact_vs_reference_fixtures():
+    g = _load("pflineart_kat.npz")
+    for k in range(int(g["ncases"])):
+        N, mode, thr = int(g[f"N{k}"]), int(g[f"mode{k}"]), float(g[f"thr{k}"])
+        r = H.o_pflineart(g[f"data{k}"], N, mode, thr, z=g[f"z{k}"], U=g[f"U{k}"])
+        assert np.array_equal(r["resampled"], g[f"resampled{k}"])
+        assert 0 < r["resampled"].sum() <= r["resampled"].size
+        for key in ("Xm", "Xv", "Ym", "Yv", "logNC"):
+            assert np.array_equal(r[key], g[f"{key}{k}"]), f"case {k} {key}"
+        assert np.array_equal(r["ESS"][1:], g[f"ESS{k}"][1:])

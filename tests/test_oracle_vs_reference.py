@@ -63,3 +63,18 @@ def test_pfnonlinbs_traces(N, T, mode, thr):
     for key in ("mean", "sd", "logNC"):
         assert np.array_equal(r[key], o[key])
     assert np.array_equal(r["ESS"][1:], o["ESS"][1:])
+
+
+@pytest.mark.parametrize("N,T,mode,thr", [(500, 40, H.SYSTEMATIC, 0.5), (300, 30, H.STRATIFIED, 0.5), (200, 25, H.SYSTEMATIC, 201.0),
+                                           (2, 6, H.STRATIFIED, 0.9)])
+def test_pflineart_traces(N, T, mode, thr):
+    # ESS-triggered resampling (threshold 0.5 N as in the reference driver) and always-resample
+    rng = np.random.default_rng(3 * N + T)
+    data = H.sim_lineart(T, N)
+    z, U = rng.standard_normal(4 * N * T), rng.random(T * (N + 1))
+    r = H.r_pflineart(data, N, mode, thr, z, U)
+    o = H.o_pflineart(data, N, mode, thr, z=z, U=U)
+    assert np.array_equal(r["resampled"], o["resampled"])
+    for key in ("Xm", "Xv", "Ym", "Yv", "logNC"):
+        assert np.array_equal(r[key], o[key]), key
+    assert np.array_equal(r["ESS"][1:], o["ESS"][1:])
