@@ -83,6 +83,14 @@ int smcb200_pfNonlinBS(const double* data_host, long T, long particles, int resa
  * filter itself.  `stream` is a cudaStream_t (NULL = default stream); all work of the handle is enqueued there. */
 typedef struct smcb200_pf smcb200_pf;
 int smcb200_pfNonlinBS_create(long particles, long tcap, uint64_t seed, void* stream, smcb200_pf** out);
+/* Island mode (one process per GPU on one NVSwitch box): rank `rank` of `world` owns particles_local particles of ONE
+ * population of world*particles_local particles with GLOBAL resampling.  Each rank exports one 64-byte CUDA IPC handle
+ * (ipc_export), the host all-gathers them (any transport) and hands all `world` handles to ipc_import; after that the
+ * kernels exchange per-step scalars and remote parents directly over NVLink peer memory.  Every rank must use the same
+ * seed, data and run() arguments; read() returns identical traces on every rank.  SYSTEMATIC / STRATIFIED only. */
+int smcb200_pfNonlinBS_create_island(long particles_local, long tcap, uint64_t seed, void* stream, int rank, int world, smcb200_pf** out);
+int smcb200_pfNonlinBS_ipc_export(smcb200_pf* h, void* handle64_out);
+int smcb200_pfNonlinBS_ipc_import(smcb200_pf* h, const void* handles_world_x64);
 int smcb200_pfNonlinBS_set_data(smcb200_pf* h, const double* data_host, long T);
 int smcb200_pfNonlinBS_set_noise(smcb200_pf* h, const double* noise_host, const double* uniforms_host, long n_uniforms);
 /* Enqueues Initialise + (T-1) Iterate + the final moment pass; asynchronous. */

@@ -53,6 +53,10 @@ def lib():
                                       _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
+    L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.smcb200_pfNonlinBS_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.smcb200_pfNonlinBS_ipc_import.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.smcb200_pfNonlinBS_set_data.argtypes = [ctypes.c_void_p, _c_double_p, ctypes.c_long]
     L.smcb200_pfNonlinBS_set_noise.argtypes = [ctypes.c_void_p, _c_double_p, _c_double_p, ctypes.c_long]
     L.smcb200_pfNonlinBS_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
@@ -186,11 +190,25 @@ def pfLineartBS(data, particles, usef=False, fun=None, resample_mode=RESIDUAL, t
 class PfNonlinBS:
     """Handle-based filter: device buffers persist across runs (benchmarking, repeated filtering)."""
 
-    def __init__(self, particles, tcap, seed=1, stream=None):
+    def __init__(self, particles, tcap, seed=1, stream=None, island=None):
+        """``island=(rank, world)``: this process owns ``particles`` particles of one population of ``world * particles``
+        with global resampling (one process per GPU); exchange ``ipc_handle()`` between ranks and ``connect()``."""
         self._h = ctypes.c_void_p()
         self.particles, self.tcap = particles, tcap
-        _check(lib().smcb200_pfNonlinBS_create(particles, tcap, seed, stream, ctypes.byref(self._h)))
+        if island is None:
+            _check(lib().smcb200_pfNonlinBS_create(particles, tcap, seed, stream, ctypes.byref(self._h)))
+        else:
+            _check(lib().smcb200_pfNonlinBS_create_island(particles, tcap, seed, stream, island[0], island[1], ctypes.byref(self._h)))
         self.T = 0
+
+    def ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        _check(lib().smcb200_pfNonlinBS_ipc_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
+        _check(lib().smcb200_pfNonlinBS_ipc_import(self._h, blob))
 
     def set_data(self, data):
         y = _f64(data)

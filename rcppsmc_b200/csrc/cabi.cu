@@ -186,7 +186,7 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
             DevBuf w(sizeof(double) * n);
             SMCB_CUDA(cudaMemcpy(w.p, weights_host, sizeof(double) * n, cudaMemcpyHostToDevice));
             ScanArgs a{};
-            a.in = w.as<double>(); a.n = n; a.u_ptr = u_dev; a.ticket = ticket; a.ws = ws; a.am = am;
+            a.in = w.as<double>(); a.n = n; a.n_glob = n; a.u_ptr = u_dev; a.ticket = ticket; a.ws = ws; a.am = am;
             a.count_out = counts.as<int>(); a.tail_info = tail;
             DevBuf us;
             if (mode == SMCB200_SYSTEMATIC) {
@@ -233,6 +233,40 @@ int smcb200_pfNonlinBS_create(long particles, long tcap, uint64_t seed, void* st
         SMCB_CUDA(cudaEventCreate(&h->ev0));
         SMCB_CUDA(cudaEventCreate(&h->ev1));
         *out = h.release();
+        return SMCB200_OK;
+    });
+}
+
+int smcb200_pfNonlinBS_create_island(long particles_local, long tcap, uint64_t seed, void* stream, int rank, int world, smcb200_pf** out) {
+    return guarded([&]() -> int {
+        if (!out) throw std::invalid_argument("smcb200_pfNonlinBS_create_island: out required");
+        if (particles_local < 2 || tcap < 1) throw std::invalid_argument("smcb200_pfNonlinBS_create_island: particles_local >= 2 and tcap >= 1 required");
+        require_device();
+        std::unique_ptr<smcb200_pf> h(new smcb200_pf);
+        h->n = particles_local; h->tcap = tcap; h->seed = seed; h->stream = (cudaStream_t)stream;
+        h->s.reset(new Sampler<NonlinBS>(particles_local, tcap, seed, h->stream, rank, world));
+        h->y = DevBuf(sizeof(double) * tcap);
+        h->cterm = DevBuf(sizeof(double) * tcap);
+        SMCB_CUDA(cudaEventCreate(&h->ev0));
+        SMCB_CUDA(cudaEventCreate(&h->ev1));
+        *out = h.release();
+        return SMCB200_OK;
+    });
+}
+
+int smcb200_pfNonlinBS_ipc_export(smcb200_pf* h, void* handle64_out) {
+    return guarded([&]() -> int {
+        if (!h || !handle64_out) throw std::invalid_argument("null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+        h->s->ExportIpc((cudaIpcMemHandle_t*)handle64_out);
+        return SMCB200_OK;
+    });
+}
+
+int smcb200_pfNonlinBS_ipc_import(smcb200_pf* h, const void* handles_world_x64) {
+    return guarded([&]() -> int {
+        if (!h || !handles_world_x64) throw std::invalid_argument("null argument");
+        h->s->ImportPeers((const cudaIpcMemHandle_t*)handles_world_x64);
         return SMCB200_OK;
     });
 }
@@ -301,7 +335,7 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
         for (long t = 1; t < h->T; ++t) s.Iterate();
         s.ObserveFinal();
         SMCB_CUDA(cudaEventRecord(h->ev1, h->stream));
-        h->launches = h->T * ((resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 2 : 4) + 1;
+        h->launches = h->T * (s.island() ? 3 : (resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 2 : 4) + 1;
         h->ran = true;
         return SMCB200_OK;
     });
@@ -369,6 +403,7 @@ int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launc
     return guarded([&]() -> int {
         if (!h || !move_ms || !move_launches || !scan_ms || !scan_launches) throw std::invalid_argument("null argument");
         if (!h->ran || !h->profile || h->kev_used < 3) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: run with profiling enabled first");
+        if (h->s->island()) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: not available in island mode");
         if (h->mode != SMCB200_SYSTEMATIC && h->mode != SMCB200_STRATIFIED) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: per-kernel split is defined for SYSTEMATIC / STRATIFIED runs");
         SMCB_CUDA(cudaEventSynchronize(h->kev[h->kev_used - 1]));
         // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1

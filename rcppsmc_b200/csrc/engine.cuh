@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "resample.cuh"
+#include "island.cuh"
 
 namespace smcb {
 
@@ -50,6 +51,10 @@ struct Ctrl {
     unsigned int ticket2;   // second ticket (count-map kernel of the MULTINOMIAL / RESIDUAL path)
     int n_accepted;
     unsigned long long floor_total;  // RESIDUAL: deterministic children handed out this step
+    // island mode (one rank of a partitioned population)
+    unsigned long long mass_offset;  // integer weight mass of all lower ranks (start of this rank's cumulative scan)
+    long long zoff[ISL_MAX + 1];     // zero-count slots before each rank (exclusive prefix; [world] = total)
+    long long eoff[ISL_MAX + 1];     // surplus-list entries before each rank
 };
 
 struct Traces {             // device arrays of length Tcap
@@ -77,11 +82,12 @@ struct StepArgs {
     const double* ures;         // injected resampling base uniforms, one per step, or null
     long long tcap;
     int dbg;                    // experiment switches (0 in production): 1 identity ancestors, 2 no stores, 4 no RNG, 8 no LSE
+    IslandInfo isl;             // island mode only
 };
 
 enum { PHASE_INIT = 0, PHASE_MOVE = 1, PHASE_OBSERVE = 2 };
 
-template <class Model, int PHASE, bool INJECT>
+template <class Model, int PHASE, bool INJECT, bool ISLAND = false>
 __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
     constexpr int D = Model::D, G = Model::NSHIFT, NOBS = Model::NOBS;
     constexpr int NZ = PHASE == PHASE_INIT ? Model::NZ_INIT : Model::NZ_MOVE;
@@ -140,14 +146,33 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     auto stageB = [&](long long p) {   // consumes mA/bA (loaded for this p one iteration ago)
         if (PHASE != PHASE_INIT && p < npairs) {
             const long long s0 = 2 * p;
-            ancB[0] = (uint32_t)s0; ancB[1] = (uint32_t)(s0 + 1);
+            const uint32_t self0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc + s0) : (uint32_t)s0;   // global slot id
+            ancB[0] = self0; ancB[1] = self0 + 1u;
             if (resampled && !(a.dbg & 1)) {
                 const uint32_t bit = (uint32_t)s0 & 31u;
                 const uint32_t below = mA & ((1u << bit) - 1u);
                 const uint32_t rank = bA + __popc(below);
                 const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
-                if (z0) ancB[0] = __ldg(a.am.surplus + rank);
-                if (z1) ancB[1] = __ldg(a.am.surplus + rank + z0);
+                if (!ISLAND) {
+                    if (z0) ancB[0] = __ldg(a.am.surplus + rank);
+                    if (z1) ancB[1] = __ldg(a.am.surplus + rank + z0);
+                } else {
+                    // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 0 ? z0 : z1) {
+                            const long long m = a.ctrl->zoff[a.isl.rank] + rank + (h ? z0 : 0u);
+                            uint32_t par = 0u;   // beyond the available surplus children: particle 0 (sampler.h:845)
+                            if (m < a.ctrl->eoff[a.isl.world]) {
+                                int o = 0;
+                                while (o + 1 < a.isl.world && m >= a.ctrl->eoff[o + 1]) ++o;
+                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.isl.base[o] + a.isl.off_surplus);
+                                par = sp[m - a.ctrl->eoff[o]];
+                            }
+                            ancB[h] = par;
+                        }
+                    }
+                }
             }
         }
     };
@@ -155,10 +180,24 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         if (PHASE != PHASE_INIT && p < npairs) {
             const long long s0 = 2 * p;
             const bool has1 = s0 + 1 < n;
+            if (!ISLAND) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                xC[0][d] = src[d][ancB[0]];
-                xC[1][d] = has1 ? src[d][ancB[1]] : 0.0;
+                for (int d = 0; d < D; ++d) {
+                    xC[0][d] = src[d][ancB[0]];
+                    xC[1][d] = has1 ? src[d][ancB[1]] : 0.0;
+                }
+            } else {
+                // the parent may live on another island: read it from the owner's slab over NVLink
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int o = (int)(ancB[h] / (uint32_t)a.isl.n_loc);
+                    const long long li = (long long)ancB[h] - (long long)o * a.isl.n_loc;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const double* xs = reinterpret_cast<const double*>(a.isl.base[o] + (parity ? a.isl.off_xb[d] : a.isl.off_xa[d]));
+                        xC[h][d] = (h == 0 || has1) ? xs[li] : 0.0;
+                    }
+                }
             }
             if (!resampled) { lwC[0] = a.lw[s0]; lwC[1] = has1 ? a.lw[s0 + 1] : 0.0; }
         }
@@ -210,7 +249,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
 #pragma unroll
                 for (int k = 0; k < NZ; ++k) {
                     if (a.dbg & 4) { z[0][k] = 0.3 + 1e-9 * (double)p; z[1][k] = -0.2; }
-                    else philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur, (uint64_t)p, k, z[0][k], z[1][k]);
+                    else philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur,
+                                        (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) + p : p), k, z[0][k], z[1][k]);
                 }
             }
 #pragma unroll
@@ -305,6 +345,32 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         o0 = warp_sum(o0);
 #pragma unroll
         for (int j = 0; j < NOBS; ++j) o[j] = warp_sum(o[j]);
+        if (ISLAND) {
+            // all-gather the per-island tuples through the peer mailboxes and merge them in rank order (same bits on every rank)
+            static_assert(4 + G + NOBS <= ISL_PAYLOAD, "island message too small for this model");
+            __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
+            double mine[ISL_PAYLOAD];
+            mine[0] = b.m; mine[1] = b.s; mine[2] = b.q; mine[3] = o0;
+#pragma unroll
+            for (int j = 0; j < G; ++j) mine[4 + j] = b.g[j];
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) mine[4 + G + j] = o[j];
+            const unsigned long long seq = (a.isl.epoch << 24) + (unsigned long long)(PHASE == PHASE_OBSERVE ? T : tcur) + 1ull;
+            island_allgather(a.isl, PHASE == PHASE_OBSERVE ? ISL_KIND_OBS : ISL_KIND_LSE, seq, mine, 4 + G + NOBS, s_all);
+            b.clear(); o0 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
+            for (int h = 0; h < a.isl.world; ++h) {
+                LseAcc<G> t;
+                t.m = s_all[h][0]; t.s = s_all[h][1]; t.q = s_all[h][2];
+#pragma unroll
+                for (int j = 0; j < G; ++j) t.g[j] = s_all[h][4 + j];
+                b.merge(t);
+                o0 += s_all[h][3];
+#pragma unroll
+                for (int j = 0; j < NOBS; ++j) o[j] += s_all[h][4 + G + j];
+            }
+        }
         if (lane == 0) {
             Ctrl* c = a.ctrl;
             if (PHASE != PHASE_INIT && NOBS > 0 && T < a.tcap) {
@@ -359,35 +425,84 @@ class Sampler {
 public:
     static constexpr int D = Model::D, NOBS = Model::NOBS, G = Model::NSHIFT;
 
-    Sampler(long long n, long long tcap, unsigned long long seed, cudaStream_t stream = 0)
-        : n_(n), tcap_(tcap), seed_(seed), stream_(stream) {
+    // n = particles owned by this process.  world > 1 selects island mode: this rank owns global slots
+    // [rank n, (rank+1) n) of a population of world*n particles; every array peers must reach lives in ONE slab so that a
+    // single CUDA IPC handle per rank is enough (ExportIpc / ImportPeers).
+    Sampler(long long n, long long tcap, unsigned long long seed, cudaStream_t stream = 0, int rank = 0, int world = 1)
+        : n_(n), tcap_(tcap), seed_(seed), stream_(stream), rank_(rank), world_(world) {
         if (n < 1 || n > 2147483647LL) throw std::invalid_argument("particle count must be in [1, 2^31)");
+        if (world < 1 || world > ISL_MAX || rank < 0 || rank >= world) throw std::invalid_argument("island rank/world out of range");
+        n_glob_ = n * world;
+        if (world > 1 && (n_glob_ > 2147483647LL || (n & 1))) throw std::invalid_argument("island mode needs an even local particle count and world*n < 2^31");
         ntiles_ = scan_tiles(n);
-        for (int d = 0; d < D; ++d) { xa_[d] = dalloc<double>(n); xb_[d] = dalloc<double>(n); }
-        lw_ = dalloc<double>(n);
-        am_.zmask = dalloc<uint32_t>((n + 31) / 32 + 64);
-        am_.zbase = dalloc<uint32_t>((n + 31) / 32 + 64);
-        am_.surplus = dalloc<uint32_t>(n);
-        status_ = dalloc<unsigned long long>(3 * ntiles_);
-        ctrl_ = dalloc<Ctrl>(1);
-        tr_.lognc = dalloc<double>(tcap); tr_.ess = dalloc<double>(tcap);
-        tr_.resampled = dalloc<int>(tcap); tr_.obs = dalloc<double>(tcap * (NOBS > 0 ? NOBS : 1));
+        surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
+        // ---- slab layout (256-byte aligned sub-allocations)
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+        size_t o_xa[D], o_xb[D];
+        for (int d = 0; d < D; ++d) { o_xa[d] = take(sizeof(double) * n); o_xb[d] = take(sizeof(double) * n); }
+        size_t o_lw = take(sizeof(double) * n);
+        size_t o_zm = take(sizeof(uint32_t) * ((n + 31) / 32 + 64)), o_zb = take(sizeof(uint32_t) * ((n + 31) / 32 + 64));
+        size_t o_su = take(sizeof(uint32_t) * surplus_cap_);
+        size_t o_st = take(sizeof(unsigned long long) * 3 * ntiles_);
+        size_t o_ct = take(sizeof(Ctrl));
+        size_t o_t0 = take(sizeof(double) * tcap), o_t1 = take(sizeof(double) * tcap), o_t2 = take(sizeof(int) * tcap);
+        size_t o_t3 = take(sizeof(double) * tcap * (NOBS > 0 ? NOBS : 1));
+        size_t o_mb = take(sizeof(IslMsg) * ISL_KINDS * 2 * ISL_MAX);
         grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
         grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
         grid_scan_ = resample_scan_grid<SRC_LOGW, SYSTEMATIC>(n);
         int gmax = grid_init_ > grid_move_ ? grid_init_ : grid_move_;
-        partial_ = dalloc<double>((size_t)(4 + G + NOBS) * gmax);
-        SMCB_CUDA(cudaMemsetAsync(status_, 0, sizeof(unsigned long long) * 3 * ntiles_, stream_));
+        size_t o_pa = take(sizeof(double) * (size_t)(4 + G + NOBS) * gmax);
+        size_t o_mp = take(sizeof(unsigned long long) * 1024);
+        slab_bytes_ = off;
+        void* base = nullptr;
+        SMCB_CUDA(cudaMalloc(&base, slab_bytes_));
+        allocs_.push_back(base);
+        slab_ = (unsigned char*)base;
+        SMCB_CUDA(cudaMemsetAsync(slab_ + o_st, 0, sizeof(unsigned long long) * 3 * ntiles_, stream_));
+        SMCB_CUDA(cudaMemsetAsync(slab_ + o_mb, 0, sizeof(IslMsg) * ISL_KINDS * 2 * ISL_MAX, stream_));
+        SMCB_CUDA(cudaMemsetAsync(slab_ + o_mp, 0, sizeof(unsigned long long) * 1024, stream_));
+        for (int d = 0; d < D; ++d) { xa_[d] = (double*)(slab_ + o_xa[d]); xb_[d] = (double*)(slab_ + o_xb[d]); }
+        lw_ = (double*)(slab_ + o_lw);
+        am_.zmask = (uint32_t*)(slab_ + o_zm); am_.zbase = (uint32_t*)(slab_ + o_zb); am_.surplus = (uint32_t*)(slab_ + o_su);
+        status_ = (unsigned long long*)(slab_ + o_st);
+        ctrl_ = (Ctrl*)(slab_ + o_ct);
+        tr_.lognc = (double*)(slab_ + o_t0); tr_.ess = (double*)(slab_ + o_t1); tr_.resampled = (int*)(slab_ + o_t2); tr_.obs = (double*)(slab_ + o_t3);
+        partial_ = (double*)(slab_ + o_pa);
+        mass_partial_ = (unsigned long long*)(slab_ + o_mp);
+        isl_ = IslandInfo{};
+        isl_.rank = rank; isl_.world = world; isl_.n_loc = n; isl_.n_glob = n_glob_;
+        for (int d = 0; d < D; ++d) { isl_.off_xa[d] = o_xa[d]; isl_.off_xb[d] = o_xb[d]; }
+        isl_.off_surplus = o_su; isl_.off_mailbox = o_mb;
+        isl_.base[rank] = slab_;
+        peers_ready_ = world == 1;
         SetResampleParams(STRATIFIED, 0.5);  // reference defaults, sampler.h:259-267
     }
-    ~Sampler() { for (void* p : allocs_) cudaFree(p); }
+    ~Sampler() {
+        for (int h = 0; h < world_; ++h) if (h != rank_ && isl_.base[h]) cudaIpcCloseMemHandle(isl_.base[h]);
+        for (void* p : allocs_) cudaFree(p);
+    }
     Sampler(const Sampler&) = delete;
     Sampler& operator=(const Sampler&) = delete;
+
+    // ---- island plumbing: one IPC handle per rank, exchanged by the host (torch.distributed in bench.py / tests)
+    bool island() const { return world_ > 1; }
+    void ExportIpc(cudaIpcMemHandle_t* out) { SMCB_CUDA(cudaIpcGetMemHandle(out, slab_)); }
+    void ImportPeers(const cudaIpcMemHandle_t* handles) {
+        for (int h = 0; h < world_; ++h) {
+            if (h == rank_) continue;
+            void* p = nullptr;
+            SMCB_CUDA(cudaIpcOpenMemHandle(&p, handles[h], cudaIpcMemLazyEnablePeerAccess));
+            isl_.base[h] = (unsigned char*)p;
+        }
+        peers_ready_ = true;
+    }
 
     // sampler.h:885-893
     void SetResampleParams(int mode, double threshold) {
         mode_ = mode;
-        thr_ = threshold < 1 ? threshold * (double)n_ : threshold;
+        thr_ = threshold < 1 ? threshold * (double)n_glob_ : threshold;
     }
     void SetParams(const typename Model::Params& p) { params_ = p; }
     void SetSeed(unsigned long long seed) { seed_ = seed; }
@@ -399,10 +514,13 @@ public:
     // sampler.h:481-550 (up to and including the resampling decision; the resampling pass itself is enqueued here too)
     void Initialise() {
         Ctrl h{};
-        h.thr = thr_; h.log_n = std::log((double)n_); h.parity = 1;  // init writes buffer A (dst of parity 1)
+        if (!peers_ready_) throw std::runtime_error("island sampler: ImportPeers() has not been called");
+        ++isl_.epoch;
+        h.thr = thr_; h.log_n = std::log((double)n_glob_); h.parity = 1;  // init writes buffer A (dst of parity 1)
         SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
         StepArgs<Model> a = args();
-        if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
+        if (island()) { no_inject(); k_step<Model, PHASE_INIT, false, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a); }
+        else if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
         else k_step<Model, PHASE_INIT, false><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
         if (after_launch_) after_launch_();
@@ -412,7 +530,8 @@ public:
     // sampler.h:701-764
     void Iterate() {
         StepArgs<Model> a = args();
-        if (znoise_) k_step<Model, PHASE_MOVE, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        if (island()) k_step<Model, PHASE_MOVE, false, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        else if (znoise_) k_step<Model, PHASE_MOVE, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         else k_step<Model, PHASE_MOVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
         if (after_launch_) after_launch_();
@@ -423,7 +542,8 @@ public:
     // Fused Integrate for the current (last) population: closes the observable trace.
     void ObserveFinal() {
         StepArgs<Model> a = args();
-        k_step<Model, PHASE_OBSERVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        if (island()) k_step<Model, PHASE_OBSERVE, false, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
+        else k_step<Model, PHASE_OBSERVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
         SMCB_CUDA(cudaGetLastError());
         if (after_launch_) after_launch_();
     }
@@ -466,6 +586,9 @@ public:
     int grid_scan() const { return grid_scan_; }
 
 private:
+    void no_inject() const {
+        if (znoise_ || ures_ || ustrat_ || udraw_) throw std::invalid_argument("island mode does not take injected draws");
+    }
     template <class T> T* dalloc(size_t count) {
         void* p = nullptr;
         SMCB_CUDA(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
@@ -482,7 +605,7 @@ private:
         for (int d = 0; d < D; ++d) { a.xa[d] = xa_[d]; a.xb[d] = xb_[d]; }
         a.lw = lw_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
         a.status = status_; a.nstatus = 3 * ntiles_; a.params = params_; a.seed = seed_;
-        a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_;
+        a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_; a.isl = isl_;
         { const char* e = getenv("SMCB200_DBGS"); a.dbg = e ? atoi(e) : 0; }
         return a;
     }
@@ -493,6 +616,24 @@ private:
         s.ws.statusA = status_; s.ws.statusB = status_ + ntiles_; s.ws.statusC = status_ + 2 * ntiles_;
         s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
         { const char* e = getenv("SMCB200_DBG"); s.dbg = e ? atoi(e) : 0; }
+        s.n_glob = n_glob_; s.surplus_cap = surplus_cap_; s.isl = isl_;
+        if (island()) {
+            if (mode_ != SYSTEMATIC && mode_ != STRATIFIED)
+                throw std::invalid_argument("island mode supports SYSTEMATIC and STRATIFIED resampling");
+            // where does this rank's cumulative weight start?  integer mass of the lower ranks (all-gathered in-kernel)
+            MassArgs m{};
+            m.lw = lw_; m.n = n_; m.lse_ptr = &ctrl_->lse; m.enable_ptr = &ctrl_->resampled; m.step_ptr = &ctrl_->T;
+            m.partial = mass_partial_ + 8; m.done = (unsigned int*)mass_partial_; m.mass_offset_out = &ctrl_->mass_offset; m.isl = isl_;
+            int g = grid_move_ < 1000 ? grid_move_ : 1000;
+            k_mass_total<<<g, 256, 0, stream_>>>(m);
+            SMCB_CUDA(cudaGetLastError());
+            if (after_launch_) after_launch_();
+            s.mass_offset_ptr = &ctrl_->mass_offset; s.zoff_out = ctrl_->zoff; s.eoff_out = ctrl_->eoff;
+            if (mode_ == SYSTEMATIC) launch_resample_scan<SRC_LOGW, SYSTEMATIC, true>(s, stream_);
+            else launch_resample_scan<SRC_LOGW, STRATIFIED, true>(s, stream_);
+            if (after_launch_) after_launch_();
+            return;
+        }
         switch (mode_) {
             case SYSTEMATIC: launch_resample_scan<SRC_LOGW, SYSTEMATIC>(s, stream_); break;
             case STRATIFIED: launch_resample_scan<SRC_LOGW, STRATIFIED>(s, stream_); break;
@@ -510,7 +651,13 @@ private:
         if (after_launch_) after_launch_();
     }
 
-    long long n_, tcap_, ntiles_;
+    long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
+    int rank_ = 0, world_ = 1;
+    unsigned char* slab_ = nullptr;
+    size_t slab_bytes_ = 0;
+    IslandInfo isl_{};
+    bool peers_ready_ = true;
+    unsigned long long* mass_partial_ = nullptr;
     unsigned long long seed_;
     cudaStream_t stream_;
     int mode_ = STRATIFIED;

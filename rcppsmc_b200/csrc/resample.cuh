@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
+#include "island.cuh"
 
 namespace smcb {
 
@@ -216,16 +217,23 @@ struct ScanArgs {
     int* count_out;           // optional: children counts per parent
     unsigned int* tail_info;  // optional [2]: {sum of counts, number of zero-count slots}
     int dbg;                  // experiment switches (0 in production): 1 skip look-back A, 2 skip look-back B, 4 skip exp, 8 skip surplus
+    // island mode: n = local slots, n_glob = N of the whole population; the scan starts at *mass_offset_ptr
+    long long n_glob;
+    long long surplus_cap;    // entries the surplus array can hold (0 = n)
+    const unsigned long long* mass_offset_ptr;
+    long long* zoff_out;      // [world+1] written by the last tile after the all-gather of (zero slots, surplus entries)
+    long long* eoff_out;
+    IslandInfo isl;
 };
 
 enum { SRC_LOGW = 0, SRC_WEIGHTS = 1 };
 
 template <int MODE>
-__device__ __forceinline__ long long children_upto(unsigned long long cum, const ScanArgs& a, double nd, double inv_n,
+__device__ __forceinline__ long long children_upto(unsigned long long cum, const ScanArgs& a, long long nthr, double nd, double inv_n,
                                                    double dRand, bool pow2, long long step) {
     double W = u64_to_double_exact(cum) * INV_TWO52;  // exact: cum < 2^53
     if (MODE == SYSTEMATIC) {
-        return children_below(W - dRand, a.n, nd, pow2);
+        return children_below(W - dRand, nthr, nd, pow2);
     } else {
         // STRATIFIED: child j compares against its own u_j = (1/N) U_j; only the stratum holding W is undecided.
         double g = W * nd;
@@ -233,7 +241,7 @@ __device__ __forceinline__ long long children_upto(unsigned long long cum, const
         long long js = (long long)fmin(fl, nd);
         double fr = g - fl;
         long long lo = js - 1 < 0 ? 0 : js - 1;
-        long long hi = js + 1 > a.n - 1 ? a.n - 1 : js + 1;
+        long long hi = js + 1 > nthr - 1 ? nthr - 1 : js + 1;
         long long c = lo;
         for (long long j = lo; j <= hi; ++j) {
             bool sure_true = (j < js) && fr >= 9.5367431640625e-07;
@@ -242,7 +250,7 @@ __device__ __forceinline__ long long children_upto(unsigned long long cum, const
             if (sure_true) p = true;
             else if (sure_false) p = false;
             else {
-                double U = a.ustrat ? a.ustrat[step * (a.n + 1) + j]
+                double U = a.ustrat ? a.ustrat[step * (nthr + 1) + j]
                                     : u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 0).a);
                 double uj = 0.0 + (inv_n - 0.0) * U;
                 p = (W - uj) > ((double)j / nd);
@@ -280,7 +288,8 @@ static __device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ s
 // E[k], e[k] are recomputed from the lane's running values in this rarely taken path.
 template <int ITEMS>
 __device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus, unsigned hbits, const int (&cnt)[ITEMS],
-                                                  long long cfirst, long long zexcl, unsigned zbits, long long g0, long long cap) {
+                                                  long long cfirst, long long zexcl, unsigned zbits, long long g0, long long cap,
+                                                  uint32_t id0 = 0u) {
     const int lane = threadIdx.x & 31;
     unsigned any;
     while ((any = __ballot_sync(SMCB_FULL, hbits != 0u)) != 0u) {
@@ -293,7 +302,7 @@ __device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus
             long long ck1 = cfirst, zk = zexcl;
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
-                if (k == kk) { hE = ck1 - (g0 + k) + zk + SURPLUS_SMALL; hend = hE + (cnt[k] - 1 - SURPLUS_SMALL); hk = (uint32_t)(g0 + k); }
+                if (k == kk) { hE = ck1 - (g0 + k) + zk + SURPLUS_SMALL; hend = hE + (cnt[k] - 1 - SURPLUS_SMALL); hk = id0 + (uint32_t)(g0 + k); }
                 ck1 += cnt[k];
                 zk += (zbits >> k) & 1u;
             }
@@ -328,7 +337,7 @@ struct ScanSmem {
 };
 constexpr size_t SCAN_SMEM_BYTES = sizeof(ScanSmem);
 
-template <int SRC, int MODE>
+template <int SRC, int MODE, bool ISLAND = false>
 __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(ScanArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     if (a.dbg & 16) return;
@@ -336,14 +345,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long n = a.n;
-    const double nd = (double)n;
+    const long long n = a.n;                              // slots scanned by this rank
+    const long long nthr = ISLAND ? a.n_glob : n;          // N of the resampling thresholds j/N
+    const double nd = (double)nthr;
     const double inv_n = 1.0 / nd;
-    const bool pow2 = (n & (n - 1)) == 0;
+    const bool pow2 = (nthr & (nthr - 1)) == 0;
     const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
     const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
     const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
+    const unsigned long long mass0 = ISLAND ? *a.mass_offset_ptr : 0ull;   // weight mass owned by lower ranks
+    const long long gslot0 = ISLAND ? a.isl.rank * a.isl.n_loc : 0;         // global id of local slot 0
+    const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
+    // children handed out before this rank's first slot (0 on a single GPU)
+    const long long cstart = ISLAND ? children_upto<MODE>(mass0, a, nthr, nd, inv_n, dRand, pow2, step) : 0;
 
     // tiles held by the stages: t1 enters S1 this iteration, t2 is in S2, t3 in S3 (-1 = empty)
     int t2 = -1, t3 = -1;
@@ -406,19 +421,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
                 if (lane == 0) S.bcast[b2] = ex;
             }
             __syncthreads();
-            const unsigned long long tile_excl = S.bcast[b2];
+            const unsigned long long tile_excl = S.bcast[b2] + mass0;
             const long long base = (long long)t2 * SCAN_TILE;
             const long long g0 = base + (long long)tid * SCAN_ITEMS;
             const unsigned long long* sq = S.cum[b2];
             int* sc = S.c[b2];
             const unsigned long long thread_excl = tile_excl + (tid == 0 ? 0ull : sq[(tid - 1) * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]);
-            int cprev = (int)children_upto<MODE>(thread_excl, a, nd, inv_n, dRand, pow2, step);
+            int cprev = (int)(children_upto<MODE>(thread_excl, a, nthr, nd, inv_n, dRand, pow2, step) - cstart);
             sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS] = cprev;
             unsigned zbits = 0u;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
                 int ck = cprev;
-                if (g0 + k < n) ck = (int)children_upto<MODE>(tile_excl + sq[tid * (SCAN_ITEMS + 1) + k], a, nd, inv_n, dRand, pow2, step);
+                if (g0 + k < n) ck = (int)(children_upto<MODE>(tile_excl + sq[tid * (SCAN_ITEMS + 1) + k], a, nthr, nd, inv_n, dRand, pow2, step) - cstart);
                 if (ck == cprev && g0 + k < n) zbits |= 1u << k;
                 sc[tid * (SCAN_ITEMS + 1) + k] = ck;
                 cprev = ck;
@@ -484,25 +499,42 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
 #pragma unroll
                 for (int k = 0; k < SCAN_ITEMS; ++k) {
                     long long gk = g0 + k;
-                    write_surplus_small(a.am.surplus, ck1 - gk + zk, cnt[k] - 1, (uint32_t)gk, n);
+                    write_surplus_small(a.am.surplus, ck1 - gk + zk, cnt[k] - 1, (uint32_t)(gslot0 + gk), scap);
                     if (cnt[k] - 1 > SURPLUS_SMALL) hbits |= 1u << k;
                     ck1 += cnt[k];
                     zk += (zbits >> k) & 1u;
                 }
-                finish_heavy_runs<SCAN_ITEMS>(a.am.surplus, hbits, cnt, cfirst, zexcl, zbits, g0, n);
+                finish_heavy_runs<SCAN_ITEMS>(a.am.surplus, hbits, cnt, cfirst, zexcl, zbits, g0, scap, (uint32_t)gslot0);
             }
             if (a.count_out) {
 #pragma unroll
                 for (int k = 0; k < SCAN_ITEMS; ++k) if (g0 + k < n) a.count_out[g0 + k] = cnt[k];
             }
-            if (t3 == ntiles - 1) {  // unfilled zero-count slots copy particle 0 (reference: uRSIndices zero-initialised, :845)
+            if (t3 == ntiles - 1) {
                 __shared__ long long s_tail[2];
                 if (tid == SCAN_THREADS - 1) { s_tail[0] = sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]; s_tail[1] = zexcl + __popc(zbits); }
                 __syncthreads();
-                long long ctot = s_tail[0], ztotal = s_tail[1];
-                long long etot = ctot - n + ztotal;
-                for (long long m = etot + tid; m < ztotal; m += SCAN_THREADS) a.am.surplus[m] = 0u;
-                if (tid == 0 && a.tail_info) { a.tail_info[0] = (unsigned)ctot; a.tail_info[1] = (unsigned)ztotal; }
+                const long long ctot = s_tail[0], ztotal = s_tail[1];   // children handed out / zero-count slots on this rank
+                const long long etot = ctot - n + ztotal;               // surplus-list entries written by this rank
+                if (!ISLAND) {
+                    // unfilled zero-count slots copy particle 0 (reference: uRSIndices zero-initialised, sampler.h:845)
+                    if (!a.dbg) for (long long m = etot + tid; m < ztotal; m += SCAN_THREADS) a.am.surplus[m] = 0u;
+                    if (tid == 0 && a.tail_info) { a.tail_info[0] = (unsigned)ctot; a.tail_info[1] = (unsigned)ztotal; }
+                } else if (warp == 0) {
+                    // all-gather (zero slots, surplus entries) of every island; exclusive prefixes tell k_step's decode where
+                    // the m-th zero-count slot of the GLOBAL order finds its parent
+                    __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
+                    double mine[2] = {(double)ztotal, (double)etot};
+                    island_allgather(a.isl, ISL_KIND_ZE, (a.isl.epoch << 24) + (unsigned long long)step + 1ull, mine, 2, s_all);
+                    if (lane == 0) {
+                        long long z = 0, e = 0;
+                        for (int h = 0; h < a.isl.world; ++h) {
+                            a.zoff_out[h] = z; a.eoff_out[h] = e;
+                            z += (long long)s_all[h][0]; e += (long long)s_all[h][1];
+                        }
+                        a.zoff_out[a.isl.world] = z; a.eoff_out[a.isl.world] = e;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -513,27 +545,78 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
 }
 
 // Host-side launch helpers: the pipelined kernel needs > 48 KB of dynamic shared memory (opt-in attribute).
-template <int SRC, int MODE>
+template <int SRC, int MODE, bool ISLAND = false>
 inline int resample_scan_grid(long long n) {
     static bool configured = false;
     if (!configured) {
-        SMCB_CUDA(cudaFuncSetAttribute(k_resample_scan<SRC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+        SMCB_CUDA(cudaFuncSetAttribute(k_resample_scan<SRC, MODE, ISLAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
         configured = true;
     }
     int dev = 0, sms = 0, per_sm = 0;
     SMCB_CUDA(cudaGetDevice(&dev));
     SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_scan<SRC, MODE>, SCAN_THREADS, SCAN_SMEM_BYTES));
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_scan<SRC, MODE, ISLAND>, SCAN_THREADS, SCAN_SMEM_BYTES));
     if (per_sm < 1) per_sm = 1;
     long long need = (n + SCAN_TILE - 1) / SCAN_TILE, g = (long long)sms * per_sm;
     if (g > need) g = need;
     return (int)(g < 1 ? 1 : g);
 }
-template <int SRC, int MODE>
+template <int SRC, int MODE, bool ISLAND = false>
 inline void launch_resample_scan(const ScanArgs& a, cudaStream_t stream) {
-    int grid = resample_scan_grid<SRC, MODE>(a.n);
-    k_resample_scan<SRC, MODE><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, stream>>>(a);
+    int grid = resample_scan_grid<SRC, MODE, ISLAND>(a.n);
+    k_resample_scan<SRC, MODE, ISLAND><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, stream>>>(a);
     SMCB_CUDA(cudaGetLastError());
+}
+
+// ---- island mode: integer weight mass of this rank, all-gathered so that every rank knows where its scan starts --------
+struct MassArgs {
+    const double* lw;
+    long long n;
+    const double* lse_ptr;
+    const int* enable_ptr;
+    const long long* step_ptr;
+    unsigned long long* partial;         // [gridDim.x]
+    unsigned int* done;
+    unsigned long long* mass_offset_out;
+    IslandInfo isl;
+};
+
+static __global__ void __launch_bounds__(256) k_mass_total(MassArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const double lse = *a.lse_ptr;
+    unsigned long long sum = 0ull;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256)
+        sum += (unsigned long long)__double2ll_rn(fm_exp(a.lw[i] - lse) * TWO52);
+    __shared__ unsigned long long s_w[8];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(SMCB_FULL, sum, o);
+    if (lane == 0) s_w[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = 0ull;
+        for (int w = 0; w < 8; ++w) b += s_w[w];
+        a.partial[blockIdx.x] = b;
+        __threadfence();
+        s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+    __threadfence();
+    unsigned long long tot = 0ull;
+    for (int k = lane; k < (int)gridDim.x; k += 32) tot += reinterpret_cast<volatile unsigned long long*>(a.partial)[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(SMCB_FULL, tot, o);
+    __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
+    double mine[1] = {(double)tot};   // < 2^53: exact
+    island_allgather(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)(*a.step_ptr) + 1ull, mine, 1, s_all);
+    if (lane == 0) {
+        unsigned long long off = 0ull;
+        for (int h = 0; h < a.isl.rank; ++h) off += (unsigned long long)s_all[h][0];
+        *a.mass_offset_out = off;
+        *a.done = 0u;
+    }
 }
 
 // ---- counts -> ancestor map (injected counts, multinomial / residual paths) -----------------------------
