@@ -6,8 +6,9 @@ systematic resampling every step (BASELINE.json metric: particle-steps/sec; SURV
     python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref)
 
 One bench "step" = one complete filter (Initialise + 99 Iterate + the moment passes) over one synthetic
-observation series.  Prints ONE JSON line on rank 0.  For N > 1 launch with torch.distributed.run: every rank
-filters its own 2^24-particle population (independent filters, no data-path collective: weak scaling).
+observation series.  Prints ONE JSON line on rank 0.  For N > 1 launch with torch.distributed.run: the ranks hold the
+islands (2^24 particles each) of ONE population of N x 2^24 particles with GLOBAL systematic resampling; the per-step
+exchange (three tiny all-gathers + remote parent reads) is done by the kernels over NVLink peer memory (weak scaling).
 """
 import argparse
 import ctypes
@@ -183,7 +184,8 @@ def workload_config(gpus):
     return {"workload": f"pfNonlinBS bootstrap particle filter, 2^{LOG2_N} particles x {T_STEPS} steps per GPU, SYSTEMATIC resampling every "
                         f"step (threshold 1.01 N), HistoryType NONE, outputs mean/sd/logNC/ESS per step",
             "particles_per_gpu": 1 << LOG2_N, "time_steps": T_STEPS, "resampling": "systematic",
-            "parallelism": "1 GPU" if gpus == 1 else f"{gpus} independent filters, one per GPU (no data-path collective)",
+            "parallelism": "1 GPU" if gpus == 1 else f"island partition: one population of {gpus} x 2^{LOG2_N} particles, global systematic "
+                           f"resampling, per-step all-gathers and remote parent reads inside the kernels over NVLink peer memory (CUDA IPC)",
             "l2": "working set per step (>= 400 MB of state, weights and ancestor lists) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -218,9 +220,14 @@ def main():
     n = 1 << args.log2n
     y = synthetic_data(T_STEPS)
     stream = torch.cuda.current_stream()
-    f = smc.PfNonlinBS(n, T_STEPS, seed=1000 + rank, stream=stream.cuda_stream)
+    if world == 1:
+        f = smc.PfNonlinBS(n, T_STEPS, seed=1000, stream=stream.cuda_stream)
+    else:
+        from rcppsmc_b200 import island
+        f = smc.PfNonlinBS(n, T_STEPS, seed=1000, stream=stream.cuda_stream, island=(rank, world))
+        island.connect(f, device=torch.device("cuda", local))   # 64-byte IPC handles over the NCCL group: plumbing only
     f.set_data(y)
-    f.set_profile(True)
+    f.set_profile(world == 1)
 
     def barrier():
         if dist is not None:
@@ -243,19 +250,25 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    mv, nm, sc, ns = f.kernel_ms()  # per-kernel events of the last timed step
-    move_ms, move_n, scan_ms, scan_n = mv, nm, sc, ns
+    if world == 1:
+        move_ms, move_n, scan_ms, scan_n = f.kernel_ms()  # per-kernel events of the last timed step
     launches = f.launches() * args.steps
     out_dev = f.read()
 
-    # ---- end to end through the public one-shot call: host buffers in, host buffers out, every step
+    # ---- end to end through the public call: host buffers in, host buffers out, every step
     f.set_profile(False)
     yh = np.ascontiguousarray(y)
-    smc.pfNonlinBS(yh, n, resample_mode=SYSTEMATIC, seed=7, full=True)  # builds the cached engine of the one-shot call
+    if world == 1:
+        smc.pfNonlinBS(yh, n, resample_mode=SYSTEMATIC, seed=7, full=True)  # builds the cached engine of the one-shot call
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        out_e2e = smc.pfNonlinBS(yh, n, resample_mode=SYSTEMATIC, seed=2000 + rank * 100 + k, full=True)
+        if world == 1:
+            out_e2e = smc.pfNonlinBS(yh, n, resample_mode=SYSTEMATIC, seed=2000 + k, full=True)
+        else:   # island handle: observations host -> device, filter, traces device -> host
+            f.set_data(yh)
+            f.run(SYSTEMATIC)
+            out_e2e = f.read()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -270,14 +283,20 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        dominant = "k_step (gather + propagate + weight)" if move_ms >= scan_ms else "k_resample_scan (normalise + scan + ancestor map)"
-        per_launch_ms = (move_ms / max(1, move_n)) if move_ms >= scan_ms else (scan_ms / max(1, scan_n))
-        alg_bytes = (ALG_BYTES_MOVE if move_ms >= scan_ms else ALG_BYTES_SCAN) * n
+        if world == 1:
+            dominant = "k_step (gather + propagate + weight)" if move_ms >= scan_ms else "k_resample_scan (normalise + scan + ancestor map)"
+            per_launch_ms = (move_ms / max(1, move_n)) if move_ms >= scan_ms else (scan_ms / max(1, scan_n))
+            alg_bytes = (ALG_BYTES_MOVE if move_ms >= scan_ms else ALG_BYTES_SCAN) * n
+            tkey = "k_step" if move_ms >= scan_ms else "k_resample_scan"
+        else:   # per-kernel events are a single-GPU diagnostic: report the whole step per GPU instead
+            dominant = "whole step per GPU (k_step + k_mass_total + k_resample_scan)"
+            per_launch_ms = ms_max / args.steps / T_STEPS
+            alg_bytes = ALG_BYTES_PER_PSTEP * n
+            tkey = None
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         traffic = profiled_traffic()
-        tkey = "k_step" if move_ms >= scan_ms else "k_resample_scan"
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (traffic or {}).get(tkey), "peak_source": peak_src,
+                    "traffic": (traffic or {}).get(tkey) if tkey else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms,
                     "step_share": {"k_step_ms": move_ms, "k_resample_scan_ms": scan_ms, "filter_ms": ms_max / args.steps},
                     "whole_path": {"achieved": value / world * ALG_BYTES_PER_PSTEP / 1e9, "frac": value / world * ALG_BYTES_PER_PSTEP / 1e9 / peak,

@@ -195,6 +195,7 @@ class PfNonlinBS:
         with global resampling (one process per GPU); exchange ``ipc_handle()`` between ranks and ``connect()``."""
         self._h = ctypes.c_void_p()
         self.particles, self.tcap = particles, tcap
+        self.world = 1 if island is None else island[1]
         if island is None:
             _check(lib().smcb200_pfNonlinBS_create(particles, tcap, seed, stream, ctypes.byref(self._h)))
         else:
@@ -220,7 +221,7 @@ class PfNonlinBS:
         _check(lib().smcb200_pfNonlinBS_set_noise(self._h, _dp(z), _dp(u), 0 if u is None else u.size))
 
     def run(self, resample_mode=SYSTEMATIC, threshold=None):
-        thr = 1.01 * self.particles if threshold is None else threshold
+        thr = 1.01 * self.particles * self.world if threshold is None else threshold  # absolute thresholds refer to the whole population
         _check(lib().smcb200_pfNonlinBS_run(self._h, resample_mode, thr))
 
     def sync(self):

@@ -15,13 +15,12 @@ import helpers as H  # noqa: E402
 import rcppsmc_b200 as smc  # noqa: E402
 
 
+from rcppsmc_b200 import island  # noqa: E402
+
+
 def exchange_handles(f):
     """all-gather of the 64-byte IPC handles over the host-side process group (gloo: plumbing, not data path)"""
-    world = dist.get_world_size()
-    mine = torch.frombuffer(bytearray(f.ipc_handle()), dtype=torch.uint8)
-    out = [torch.empty(64, dtype=torch.uint8) for _ in range(world)]
-    dist.all_gather(out, mine)
-    f.connect([bytes(t.numpy().tobytes()) for t in out])
+    island.connect(f)
 
 
 def main():
