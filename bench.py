@@ -217,6 +217,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    def trace(msg):
+        if os.environ.get("SMCB_BENCH_TRACE"):
+            sys.stderr.write(f"[rank {rank}] {msg}\n"); sys.stderr.flush()
+
     n = 1 << args.log2n
     y = synthetic_data(T_STEPS)
     stream = torch.cuda.current_stream()
@@ -226,6 +230,7 @@ def main():
         from rcppsmc_b200 import island
         f = smc.PfNonlinBS(n, T_STEPS, seed=1000, stream=stream.cuda_stream, island=(rank, world))
         island.connect(f, device=torch.device("cuda", local))   # 64-byte IPC handles over the NCCL group: plumbing only
+    trace("handles connected")
     f.set_data(y)
     f.set_profile(world == 1)
 
@@ -237,7 +242,9 @@ def main():
     # ---- device-resident throughput (`value`): data and tables already in HBM
     for _ in range(args.warmup):
         f.run(SYSTEMATIC)
+    trace("warmup enqueued")
     barrier()
+    trace("warmup done")
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,6 +256,7 @@ def main():
         f.run(SYSTEMATIC)
     e1.record(stream)
     barrier()
+    trace("timed region done")
     ms = e0.elapsed_time(e1)
     if world == 1:
         move_ms, move_n, scan_ms, scan_n = f.kernel_ms()  # per-kernel events of the last timed step
@@ -271,6 +279,7 @@ def main():
             out_e2e = f.read()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    trace("e2e done")
     clk = clocks.stop()
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")

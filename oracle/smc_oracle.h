@@ -28,6 +28,7 @@ int smco_resample(int mode, const double* logw, long n, const double* U, long nU
 double smco_integrate(const double* logw, const double* f, long n);
 
 void smco_set_uniforms_by_step(int on);
+void smco_set_grid_weights(int on);
 void smco_sim_nonlin(long T, const double* z_state, const double* z_obs, double var_init,
                      double var_evol, double var_obs, double cos_offset, double* x, double* y);
 int smco_pfnonlinbs(const double* y, long T, long N, int mode, double threshold, const double* z,

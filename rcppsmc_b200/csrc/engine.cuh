@@ -31,7 +31,10 @@ constexpr int MAX_SHIFT = 4;
 #ifndef SMCB_STEP_MINB
 #define SMCB_STEP_MINB 3
 #endif
-constexpr int STEP_THREADS = 256;
+#ifndef SMCB_STEP_THREADS
+#define SMCB_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = SMCB_STEP_THREADS;
 
 // Device control block: every per-step scalar of the reference sampler lives here so that a whole filter
 // runs without host round trips.  Field meanings follow sampler.h:88-128.
@@ -253,10 +256,10 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                                         (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) + p : p), k, z[0][k], z[1][k]);
                 }
             }
+            double lwo[2] = {0.0, 0.0};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h == 1 && !has1) break;
-                long long s = s0 + h;
                 double lw;
                 if (PHASE == PHASE_INIT) {
                     Model::init(x[h], lw, a.params, z[h]);   // moveset.h:133-138
@@ -265,14 +268,21 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                     lw = lwv[h];
                     Model::move(tcur, x[h], lw, a.params, z[h]);  // moveset.h:162-168
                 }
-                if (!(a.dbg & 2)) {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) dst[d][s] = x[h][d];
-                    a.lw[s] = lw;
-                }
+                lwo[h] = lw;
                 double hs[G > 0 ? G : 1];
                 Model::shift_stat(x[h], hs);
                 if (a.dbg & 8) { acc.s += lw; acc.m = 0.0; acc.q = 1.0; } else acc.add(lw, hs);
+            }
+            if (!(a.dbg & 2)) {
+                if (has1) {   // both particles of the pair: one 16-byte store per array (s0 is even, arrays are 256-byte aligned)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0) = make_double2(x[0][d], x[1][d]);
+                    *reinterpret_cast<double2*>(a.lw + s0) = make_double2(lwo[0], lwo[1]);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) dst[d][s0] = x[0][d];
+                    a.lw[s0] = lwo[0];
+                }
             }
         }
     }

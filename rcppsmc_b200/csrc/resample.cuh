@@ -19,10 +19,10 @@
 namespace smcb {
 
 #ifndef SMCB_SCAN_THREADS
-#define SMCB_SCAN_THREADS 256
+#define SMCB_SCAN_THREADS 128
 #endif
 #ifndef SMCB_SCAN_MINB
-#define SMCB_SCAN_MINB 3
+#define SMCB_SCAN_MINB 7
 #endif
 constexpr int SCAN_THREADS = SMCB_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 8;
@@ -228,12 +228,19 @@ struct ScanArgs {
 
 enum { SRC_LOGW = 0, SRC_WEIGHTS = 1 };
 
-template <int MODE>
-__device__ __forceinline__ long long children_upto(unsigned long long cum, const ScanArgs& a, long long nthr, double nd, double inv_n,
-                                                   double dRand, bool pow2, long long step) {
-    double W = u64_to_double_exact(cum) * INV_TWO52;  // exact: cum < 2^53
+// Children handed out once the cumulative weight reaches W (a multiple of 2^-52, exact in fp64).
+// POW2: N is a power of two, so (W - u) N is exact and the count is a clamped ceiling -- straight-line fp64 code.
+template <int MODE, bool POW2>
+__device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long long nthr, double nd, double inv_n,
+                                             double dRand, long long step) {
     if (MODE == SYSTEMATIC) {
-        return children_below(W - dRand, nthr, nd, pow2);
+        if (POW2) {
+            double g = fmin(fmax((W - dRand) * nd, 0.0), nd);   // exact scaling; clamp to [0, N]
+            double t = g + TWO52;                                // round to nearest integer (low word of t)
+            double r = t - TWO52;
+            return __double2loint(t) + (r < g ? 1 : 0);          // ceil
+        }
+        return (int)children_below(W - dRand, nthr, nd, false);
     } else {
         // STRATIFIED: child j compares against its own u_j = (1/N) U_j; only the stratum holding W is undecided.
         double g = W * nd;
@@ -257,7 +264,7 @@ __device__ __forceinline__ long long children_upto(unsigned long long cum, const
             }
             c += p ? 1 : 0;
         }
-        return c;
+        return (int)c;
     }
 }
 
@@ -266,10 +273,8 @@ __device__ __forceinline__ long long children_upto(unsigned long long cum, const
 // 16-byte stores for the aligned middle of very long runs).
 constexpr int SURPLUS_SMALL = 8;
 __device__ __forceinline__ void write_surplus_small(uint32_t* __restrict__ surplus, long long E, int e, uint32_t gk, long long cap) {
-    if (e > 0) {
-        int small = e < SURPLUS_SMALL ? e : SURPLUS_SMALL;
-        for (int r = 0; r < small; ++r) if (E + r < cap) surplus[E + r] = gk;
-    }
+    const int small = e < SURPLUS_SMALL ? e : SURPLUS_SMALL;
+    for (int r = 0; r < small; ++r) if (E + r < cap) surplus[E + r] = gk;
 }
 static __device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ surplus, long long hE, long long hend, uint32_t hk, long long cap) {
     const int lane = threadIdx.x & 31;
@@ -289,7 +294,7 @@ static __device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ s
 template <int ITEMS>
 __device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus, unsigned hbits, const int (&cnt)[ITEMS],
                                                   long long cfirst, long long zexcl, unsigned zbits, long long g0, long long cap,
-                                                  uint32_t id0 = 0u) {
+                                                  uint32_t id0 = 0u) {  // cold path: 64-bit arithmetic is fine here
     const int lane = threadIdx.x & 31;
     unsigned any;
     while ((any = __ballot_sync(SMCB_FULL, hbits != 0u)) != 0u) {
@@ -326,39 +331,36 @@ inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TIL
 // Stage state lives in shared memory (double-buffered), not registers.
 constexpr int SCAN_PAD = SCAN_TILE + SCAN_TILE / SCAN_ITEMS;   // blocked layout with one pad word per thread
 struct ScanSmem {
-    unsigned long long cum[2][SCAN_PAD];   // S1 -> S2: tile-relative inclusive mass per slot (pad word: unused)
+    double cum[2][SCAN_PAD];               // S1 -> S2: tile-relative inclusive weight mass per slot (exact: multiples of 2^-52)
     int c[2][SCAN_PAD];                    // S2 -> S3: children handed out up to each slot; pad word = value before the thread's run
     int zrel[2][SCAN_THREADS];             // S2 -> S3: zero-count slots before the thread's run, tile-relative
-    unsigned long long warp_tot[SCAN_WARPS];
+    double warp_tot[SCAN_WARPS];
     int warp_z[SCAN_WARPS];
-    unsigned long long bcast[2];
+    unsigned long long bcast[2];           // S1 -> S2: tile aggregate as fixed point, then the tile's exclusive prefix
     long long zpre;
     int tile[3];
 };
 constexpr size_t SCAN_SMEM_BYTES = sizeof(ScanSmem);
 
-template <int SRC, int MODE, bool ISLAND = false>
-__global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(ScanArgs a) {
-    if (a.enable_ptr && *a.enable_ptr == 0) return;
-    if (a.dbg & 16) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
-
+// The whole scan is done in fp64 ON THE 2^-52 GRID: q = (w + 1) - 1 rounds w to a multiple of 2^-52, and every partial sum
+// stays below 2, so all additions are exact and associative -- same bits as the u64 fixed-point scan, but on the (idle)
+// fp64 pipe and without integer<->double conversions per slot.  Only the per-tile status words are fixed point.
+template <int SRC, int MODE, bool ISLAND, bool POW2>
+__device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n = a.n;                              // slots scanned by this rank
     const long long nthr = ISLAND ? a.n_glob : n;          // N of the resampling thresholds j/N
     const double nd = (double)nthr;
     const double inv_n = 1.0 / nd;
-    const bool pow2 = (nthr & (nthr - 1)) == 0;
     const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
     const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
     const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
-    const unsigned long long mass0 = ISLAND ? *a.mass_offset_ptr : 0ull;   // weight mass owned by lower ranks
-    const long long gslot0 = ISLAND ? a.isl.rank * a.isl.n_loc : 0;         // global id of local slot 0
+    const double mass0 = ISLAND ? u64_to_double_exact(*a.mass_offset_ptr) * INV_TWO52 : 0.0;   // weight mass of lower ranks
+    const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
     const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
     // children handed out before this rank's first slot (0 on a single GPU)
-    const long long cstart = ISLAND ? children_upto<MODE>(mass0, a, nthr, nd, inv_n, dRand, pow2, step) : 0;
+    const int cstart = ISLAND ? children_upto<MODE, POW2>(mass0, a, nthr, nd, inv_n, dRand, step) : 0;
 
     // tiles held by the stages: t1 enters S1 this iteration, t2 is in S2, t3 in S3 (-1 = empty)
     int t2 = -1, t3 = -1;
@@ -373,43 +375,44 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
         // ================= S1: load, quantise, block scan, publish aggregate =================
         if (t1 >= 0) {
             const long long base = (long long)t1 * SCAN_TILE;
-            unsigned long long* sq = S.cum[b1];
+            const bool full = base + SCAN_TILE <= n;
+            double* sq = S.cum[b1];
 #pragma unroll
             for (int r = 0; r < SCAN_ITEMS; ++r) {
-                int i = r * SCAN_THREADS + tid;
-                long long gi = base + i;
-                unsigned long long q = 0ull;
-                if (gi < n) {
-                    double w = (SRC == SRC_LOGW) ? fm_exp(a.in[gi] - lse) : a.in[gi];
-                    q = (unsigned long long)__double2ll_rn(w * TWO52);
+                const int i = r * SCAN_THREADS + tid;
+                double q = 0.0;
+                if (full || base + i < n) {
+                    const double w = (SRC == SRC_LOGW) ? fm_exp(a.in[base + i] - lse) : a.in[base + i];
+                    q = (w + 1.0) - 1.0;                  // round to the 2^-52 grid (ulp of [1,2))
                 }
                 sq[i + (i >> 3)] = q;
             }
             __syncthreads();
-            unsigned long long cum[SCAN_ITEMS];
+            double cum[SCAN_ITEMS];
             {
-                unsigned long long run = 0ull;
+                double run = 0.0;
 #pragma unroll
                 for (int k = 0; k < SCAN_ITEMS; ++k) { run += sq[tid * (SCAN_ITEMS + 1) + k]; cum[k] = run; }
             }
-            const unsigned long long tot = cum[SCAN_ITEMS - 1];
-            unsigned long long inc = tot;
+            const double tot = cum[SCAN_ITEMS - 1];
+            double inc = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long t = __shfl_up_sync(SMCB_FULL, inc, o);
+                double t = __shfl_up_sync(SMCB_FULL, inc, o);
                 if (lane >= o) inc += t;
             }
             if (lane == 31) S.warp_tot[warp] = inc;
             __syncthreads();
-            unsigned long long off = inc - tot, agg = 0ull;
+            double off = inc - tot, agg = 0.0;
 #pragma unroll
-            for (int w = 0; w < SCAN_WARPS; ++w) { unsigned long long v = S.warp_tot[w]; if (w < warp) off += v; agg += v; }
+            for (int w = 0; w < SCAN_WARPS; ++w) { double v = S.warp_tot[w]; if (w < warp) off += v; agg += v; }
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) sq[tid * (SCAN_ITEMS + 1) + k] = off + cum[k];
-            if (tid == 0) {  // publish: tile 0 knows its prefix, everyone else an aggregate
+            if (tid == 0) {  // publish: tile 0 knows its prefix, everyone else an aggregate (fixed point, exact)
+                const unsigned long long aggq = (unsigned long long)__double2ll_rn(agg * TWO52);
                 volatile unsigned long long* st = a.ws.statusA;
-                st[t1] = (t1 == 0 ? ST_PRE : ST_AGG) | agg;
-                S.bcast[b1] = agg;
+                st[t1] = (t1 == 0 ? ST_PRE : ST_AGG) | aggq;
+                S.bcast[b1] = aggq;
             }
         }
         __syncthreads();
@@ -421,20 +424,23 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
                 if (lane == 0) S.bcast[b2] = ex;
             }
             __syncthreads();
-            const unsigned long long tile_excl = S.bcast[b2] + mass0;
-            const long long base = (long long)t2 * SCAN_TILE;
-            const long long g0 = base + (long long)tid * SCAN_ITEMS;
-            const unsigned long long* sq = S.cum[b2];
+            const double tile_excl = u64_to_double_exact(S.bcast[b2]) * INV_TWO52 + mass0;   // exact
+            const int l0 = tid * SCAN_ITEMS;                                                   // slot within the tile
+            const bool full = (long long)(t2 + 1) * SCAN_TILE <= n;
+            const int nvalid = full ? SCAN_TILE : (int)(n - (long long)t2 * SCAN_TILE);
+            const double* sq = S.cum[b2];
             int* sc = S.c[b2];
-            const unsigned long long thread_excl = tile_excl + (tid == 0 ? 0ull : sq[(tid - 1) * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]);
-            int cprev = (int)(children_upto<MODE>(thread_excl, a, nthr, nd, inv_n, dRand, pow2, step) - cstart);
+            const double thread_excl = tile_excl + (tid == 0 ? 0.0 : sq[(tid - 1) * (SCAN_ITEMS + 1) + SCAN_ITEMS - 1]);
+            int cprev = children_upto<MODE, POW2>(thread_excl, a, nthr, nd, inv_n, dRand, step) - cstart;
             sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS] = cprev;
             unsigned zbits = 0u;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
                 int ck = cprev;
-                if (g0 + k < n) ck = (int)(children_upto<MODE>(tile_excl + sq[tid * (SCAN_ITEMS + 1) + k], a, nthr, nd, inv_n, dRand, pow2, step) - cstart);
-                if (ck == cprev && g0 + k < n) zbits |= 1u << k;
+                if (full || l0 + k < nvalid) {
+                    ck = children_upto<MODE, POW2>(tile_excl + sq[tid * (SCAN_ITEMS + 1) + k], a, nthr, nd, inv_n, dRand, step) - cstart;
+                    if (ck == cprev) zbits |= 1u << k;
+                }
                 sc[tid * (SCAN_ITEMS + 1) + k] = ck;
                 cprev = ck;
             }
@@ -466,9 +472,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
                 if (lane == 0) S.zpre = (long long)ex;
             }
             __syncthreads();
-            const long long zprefix = S.zpre;
-            const long long base = (long long)t3 * SCAN_TILE;
-            const long long g0 = base + (long long)tid * SCAN_ITEMS;
+            const int zprefix = (int)S.zpre;
+            const int g0 = t3 * SCAN_TILE + tid * SCAN_ITEMS;          // local slot id (n < 2^31)
+            const bool full = (long long)(t3 + 1) * SCAN_TILE <= n;
             const int* sc = S.c[b1];
             const int cfirst = sc[tid * (SCAN_ITEMS + 1) + SCAN_ITEMS];
             int cnt[SCAN_ITEMS];
@@ -479,36 +485,35 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
                 for (int k = 0; k < SCAN_ITEMS; ++k) {
                     int ck = sc[tid * (SCAN_ITEMS + 1) + k];
                     cnt[k] = ck - cp;
-                    if (cnt[k] == 0 && g0 + k < n) zbits |= 1u << k;
+                    if (cnt[k] == 0 && (full || (long long)g0 + k < n)) zbits |= 1u << k;
                     cp = ck;
                 }
             }
-            const long long zexcl = zprefix + S.zrel[b1][tid];
+            const int zexcl = zprefix + S.zrel[b1][tid];
             {   // zero-slot bitmap: 4 threads x 8 slots = one 32-bit word
                 unsigned m = zbits << (8 * (lane & 3));
                 m |= __shfl_xor_sync(SMCB_FULL, m, 1);
                 m |= __shfl_xor_sync(SMCB_FULL, m, 2);
-                if ((lane & 3) == 0 && g0 < n) {
+                if ((lane & 3) == 0 && (full || (long long)g0 < n)) {
                     a.am.zmask[g0 >> 5] = m;
                     a.am.zbase[g0 >> 5] = (uint32_t)zexcl;
                 }
             }
             {   // surplus list: parent k with count >= 2 owns surplus[E .. E + count - 2],  E = c(k-1) - k + Z[k]
-                long long ck1 = cfirst, zk = zexcl;
+                int E = cfirst - g0 + zexcl;
                 unsigned hbits = 0u;
 #pragma unroll
                 for (int k = 0; k < SCAN_ITEMS; ++k) {
-                    long long gk = g0 + k;
-                    write_surplus_small(a.am.surplus, ck1 - gk + zk, cnt[k] - 1, (uint32_t)(gslot0 + gk), scap);
-                    if (cnt[k] - 1 > SURPLUS_SMALL) hbits |= 1u << k;
-                    ck1 += cnt[k];
-                    zk += (zbits >> k) & 1u;
+                    const int e = cnt[k] - 1;
+                    write_surplus_small(a.am.surplus, E, e, gslot0 + (uint32_t)(g0 + k), scap);
+                    if (e > SURPLUS_SMALL) hbits |= 1u << k;
+                    E += cnt[k] - 1 + (int)((zbits >> k) & 1u);      // E[k+1] = E[k] + count[k] - 1 + z[k]
                 }
-                finish_heavy_runs<SCAN_ITEMS>(a.am.surplus, hbits, cnt, cfirst, zexcl, zbits, g0, scap, (uint32_t)gslot0);
+                finish_heavy_runs<SCAN_ITEMS>(a.am.surplus, hbits, cnt, cfirst, zexcl, zbits, g0, scap, gslot0);
             }
             if (a.count_out) {
 #pragma unroll
-                for (int k = 0; k < SCAN_ITEMS; ++k) if (g0 + k < n) a.count_out[g0 + k] = cnt[k];
+                for (int k = 0; k < SCAN_ITEMS; ++k) if ((long long)g0 + k < n) a.count_out[g0 + k] = cnt[k];
             }
             if (t3 == ntiles - 1) {
                 __shared__ long long s_tail[2];
@@ -542,6 +547,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(
         t3 = t2;
         t2 = t1;
     }
+}
+
+template <int SRC, int MODE, bool ISLAND = false>
+__global__ void __launch_bounds__(SCAN_THREADS, SMCB_SCAN_MINB) k_resample_scan(ScanArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    if (a.dbg & 16) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
+    const long long nthr = ISLAND ? a.n_glob : a.n;
+    if ((nthr & (nthr - 1)) == 0) resample_scan_body<SRC, MODE, ISLAND, true>(a, S);
+    else resample_scan_body<SRC, MODE, ISLAND, false>(a, S);
 }
 
 // Host-side launch helpers: the pipelined kernel needs > 48 KB of dynamic shared memory (opt-in attribute).

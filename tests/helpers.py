@@ -120,8 +120,9 @@ def sim_nonlin(T, seed, var_init=10.0, var_evol=10.0, var_obs=1.0, cos_offset=-1
     return x, y
 
 
-def o_pfnonlinbs(y, N, mode, threshold, z=None, U=None, seed=0, want_idx=False, by_step=False):
+def o_pfnonlinbs(y, N, mode, threshold, z=None, U=None, seed=0, want_idx=False, by_step=False, grid=False):
     oracle().smco_set_uniforms_by_step(1 if by_step else 0)
+    oracle().smco_set_grid_weights(1 if grid else 0)
     y = f64(y)
     T = y.size
     mean, sd, nc, ess = np.empty(T), np.empty(T), np.empty(T), np.empty(T)

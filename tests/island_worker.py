@@ -59,6 +59,8 @@ def main():
                 and err["mean"] < 1e-6 and err["sd"] < 1e-6
             print(f"island world={world} N=2^{log2n} T={T} mode={mode}: identical_across_ranks={same} rel_err_vs_1gpu={err} -> {'OK' if good else 'FAIL'}",
                   flush=True)
+            if not good:
+                print("  per-step logNC diff", out["logNC"] - ref["logNC"], "\n  per-step mean diff", out["mean"] - ref["mean"], flush=True)
             ok = ok and good
         f.close()
         dist.barrier()
