@@ -213,6 +213,26 @@ template <class T> struct Mat {
     void fill(T v) { std::fill(d.begin(), d.end(), v); }
     void zeros() { fill(T(0)); }
     Col<T> col(uword j) const { Col<T> r(n_rows); for (uword i = 0; i < n_rows; ++i) r.d[i] = (*this)(i, j); return r; }
+    struct ColRef {   // writable column view
+        Mat& m; uword j;
+        ColRef& operator=(const Col<T>& o) { for (uword i = 0; i < m.n_rows; ++i) m(i, j) = o.d[i]; return *this; }
+        operator Col<T>() const { Col<T> r(m.n_rows); for (uword i = 0; i < m.n_rows; ++i) r.d[i] = m(i, j); return r; }
+    };
+    ColRef col(uword j) { return ColRef{*this, j}; }
+    // "a b c; d e f" initialiser (arma::mat from a string)
+    explicit Mat(const char* txt) {
+        std::vector<std::vector<T>> rows(1);
+        std::istringstream in(txt); std::string tok;
+        while (in >> tok) {
+            bool end = !tok.empty() && tok.back() == ';';
+            if (end) tok.pop_back();
+            if (!tok.empty()) rows.back().push_back((T)std::stod(tok));
+            if (end) rows.emplace_back();
+        }
+        if (rows.back().empty()) rows.pop_back();
+        n_rows = rows.size(); n_cols = rows[0].size(); n_elem = n_rows * n_cols; d.resize(n_elem);
+        for (uword i = 0; i < n_rows; ++i) for (uword j = 0; j < n_cols; ++j) (*this)(i, j) = rows[i][j];
+    }
     Mat t() const { Mat r(n_cols, n_rows); for (uword i = 0; i < n_rows; ++i) for (uword j = 0; j < n_cols; ++j) r(j, i) = (*this)(i, j); return r; }
     // row access: a tiny proxy supporting read (as 1 x n Mat) and assignment from Col/Mat
     struct RowRef {
@@ -227,6 +247,14 @@ template <class T> struct Mat {
     Mat rows(uword a, uword b) const { Mat r(b - a + 1, n_cols); for (uword i = a; i <= b; ++i) for (uword j = 0; j < n_cols; ++j) r(i - a, j) = (*this)(i, j); return r; }
 };
 typedef Mat<double> mat;
+template <class T> struct Cube {
+    std::vector<Mat<T>> s; uword n_rows = 0, n_cols = 0, n_slices = 0;
+    Cube() {}
+    Cube(uword r, uword c, uword k) : s(k, Mat<T>(r, c)), n_rows(r), n_cols(c), n_slices(k) {}
+    Mat<T>& slice(uword k) { return s[k]; }
+    const Mat<T>& slice(uword k) const { return s[k]; }
+};
+typedef Cube<double> cube;
 template <class T> inline Mat<T> Col<T>::t() const { Mat<T> r(1, d.size()); for (size_t j = 0; j < d.size(); ++j) r(0, j) = d[j]; return r; }
 
 struct DiagView { const vec& v; };
@@ -274,10 +302,20 @@ inline double dnorm(double x, double mu, double sigma, int give_log) {
     if (give_log) return -(M_LN_SQRT_2PI_ + 0.5 * z * z + std::log(sigma));
     return std::exp(-0.5 * z * z) / (sigma * 2.50662827463100050241576528481);
 }
+// Gamma(shape, scale).  When uniforms are injected and the shape is a small integer k the draw is the sum of k
+// exponentials, -scale * sum log(u_i) (k uniforms consumed); otherwise std::gamma_distribution.  Parity-unpinned
+// like the rest of the RNG surface (R's rgamma is Marsaglia-Tsang / Ahrens-Dieter).
 inline double rgamma(double shape, double scale) {
+    shim::State& s = shim::st();
+    int k = (int)shape;
+    if (!s.uq.empty() && (double)k == shape && k >= 1 && k <= 8) {
+        double acc = 0.0;
+        for (int i = 0; i < k; ++i) acc += -std::log(shim::unif01());
+        return scale * acc;
+    }
     std::gamma_distribution<double> g(shape, scale);
-    ++shim::st().n_unif;
-    return g(shim::st().eng);
+    ++s.n_unif;
+    return g(s.eng);
 }
 }  // namespace R
 
@@ -344,6 +382,7 @@ struct NamedPH {
     Column operator=(const IntegerVector& x) const { return Column{n, std::vector<double>(x.v.begin(), x.v.end())}; }
     Column operator=(const arma::vec& x) const { return Column{n, x.d}; }
     Column operator=(const arma::mat& x) const { return Column{n, x.d}; }
+    Column operator=(const arma::cube& x) const { std::vector<double> v; for (auto& m : x.s) v.insert(v.end(), m.d.begin(), m.d.end()); return Column{n, v}; }
     Column operator=(const std::vector<double>& x) const { return Column{n, x}; }
     Column operator=(double x) const { Column c{n, {x}}; c.scalar = x; c.is_scalar = true; return c; }
 };

@@ -37,6 +37,10 @@ int smco_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
 int smco_pflineart(const double* data, long T, long N, int mode, double threshold, const double* z, const double* U,
                    unsigned long long seed, double* Xm, double* Xv, double* Ym, double* Yv, double* lognc, double* ess,
                    int* resampled);
+long smco_linreg_la(const double* data, long n_obs, long N, int adaptive, const double* temps_in, long L_in, double resampTol,
+                    double tempTol, const double* z, const double* U, unsigned long long seed, long max_temps, double* theta_out,
+                    double* ll_out, double* lp_out, double* w_out, double* ess_out, double* temps_out, double* reps_out,
+                    double* lognc_out, double* accept_out);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 
