@@ -128,6 +128,26 @@ int smcb200_pfLineartBS(const double* data_host, long T, long particles, int res
                         smcb200_step_callback callback, void* user, double* Xm_host, double* Xv_host, double* Ym_host,
                         double* Yv_host, double* lognc_host, double* ess_host, int* resampled_host);
 
+/* ---- model level: LinRegLA_adapt / LinRegLA (reference src/LinReg_LA_adapt.cpp:36-106, src/LinReg_LA.cpp:45-111) ---- */
+
+/* Likelihood-annealing SMC sampler with adaptive temperatures (CESS bisection, rho = tempTol), adaptive MCMC repeats and
+ * an empirical-covariance random-walk proposal.  `data` = arma::mat [n_obs x 2] column-major (y column, x column).
+ * Outputs use the reference's shapes with L = number of temperatures (the return value, <= max_temps):
+ *   theta [N x 3 x L] (cube, column-major), loglike / logprior / weights [N x L], ess / temps / repeats [L],
+ *   lognc4 = { logNC_standard, logNC_ps_rect, logNC_ps_trap, logNC_ps_trap2 }, accept (optional) = acceptProb per step.
+ * noise / uniforms: optional injected N(0,1) / U(0,1) streams in the reference's consumption order (Initialise: 2 normals
+ * and 3 uniforms per particle [Gamma(3) as a sum of exponentials]; per step: 1 uniform when resampling, then per MCMC
+ * repeat and particle 3 normals + 1 uniform).  Returns L > 0, or -status on failure (smcb200_last_error()). */
+long smcb200_LinRegLA_adapt(const double* data_host, long n_obs, long particles, double resampTol, double tempTol, uint64_t seed,
+                            const double* noise_host, long n_noise, const double* uniforms_host, long n_uniforms, long max_temps,
+                            double* theta_host, double* loglike_host, double* logprior_host, double* weights_host, double* ess_host,
+                            double* temps_host, double* repeats_host, double* lognc4_host, double* accept_host);
+
+/* Fixed temperature schedule temps[n_temps], proposal chol(covRW), 10 MH repeats every step, SYSTEMATIC / 0.5. */
+int smcb200_LinRegLA(const double* data_host, long n_obs, const double* temps_host, long n_temps, long particles, uint64_t seed,
+                     const double* noise_host, long n_noise, const double* uniforms_host, long n_uniforms, double* theta_host,
+                     double* loglike_host, double* logprior_host, double* weights_host, double* ess_host, double* lognc4_host);
+
 #ifdef __cplusplus
 }
 #endif

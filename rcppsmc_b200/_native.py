@@ -51,6 +51,11 @@ def lib():
     L.smcb200_pfLineartBS.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_uint64,
                                       _c_double_p, _c_double_p, ctypes.c_void_p, ctypes.c_void_p, _c_double_p, _c_double_p,
                                       _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p]
+    L.smcb200_LinRegLA_adapt.restype = ctypes.c_long
+    L.smcb200_LinRegLA_adapt.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                         _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, ctypes.c_long] + [_c_double_p] * 9
+    L.smcb200_LinRegLA.argtypes = [_c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_uint64,
+                                   _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long] + [_c_double_p] * 6
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
@@ -185,6 +190,50 @@ def pfLineartBS(data, particles, usef=False, fun=None, resample_mode=RESIDUAL, t
     if full:
         out.update(logNC=lognc, ESS=ess, resampled=res)
     return out
+
+
+def _la_data(Data):
+    d = np.asarray(Data, dtype=np.float64)
+    if d.ndim != 2 or d.shape[1] != 2:
+        raise ValueError("Data must be [n_obs x 2] (y, x)")
+    return np.ascontiguousarray(d.T.reshape(-1)), d.shape[0]   # column-major: y column then x column
+
+
+def LinRegLA_adapt(Data, lNumber, resampTol=0.5, tempTol=0.9, seed=1, noise=None, uniforms=None, max_temps=512):
+    """Mirror of ``LinRegLA_adapt_impl(Data, lNumber, resampTol, tempTol)`` (reference src/LinReg_LA_adapt.cpp:36-106).
+    Returns the reference's list: theta [N,3,L], loglike/logprior/Weights [N,L], ESS, Temps, mcmcRepeats [L] and the four
+    log-evidence estimates."""
+    flat, n_obs = _la_data(Data)
+    N = int(lNumber)
+    th = np.empty(max_temps * 3 * N); ll = np.empty(max_temps * N); lp = np.empty(max_temps * N); w = np.empty(max_temps * N)
+    ess, temps, reps, acc = (np.empty(max_temps) for _ in range(4))
+    nc = np.empty(4)
+    z, u = _f64(noise), _f64(uniforms)
+    L = lib().smcb200_LinRegLA_adapt(_dp(flat), n_obs, N, resampTol, tempTol, seed, _dp(z), 0 if z is None else z.size, _dp(u),
+                                     0 if u is None else u.size, max_temps, _dp(th), _dp(ll), _dp(lp), _dp(w), _dp(ess), _dp(temps),
+                                     _dp(reps), _dp(nc), _dp(acc))
+    if L <= 0:
+        raise SmcError(f"smcb200 status {-L}: {lib().smcb200_last_error().decode()}")
+    return {"theta": th[:L * 3 * N].reshape(L, 3, N).transpose(2, 1, 0), "loglike": ll[:L * N].reshape(L, N).T,
+            "logprior": lp[:L * N].reshape(L, N).T, "Weights": w[:L * N].reshape(L, N).T, "ESS": ess[:L].copy(), "Temps": temps[:L].copy(),
+            "mcmcRepeats": reps[:L].copy(), "logNC_standard": nc[0], "logNC_ps_rect": nc[1], "logNC_ps_trap": nc[2],
+            "logNC_ps_trap2": nc[3], "acceptProb": acc[:L].copy()}
+
+
+def LinRegLA(Data, intemps, lNumber, seed=1, noise=None, uniforms=None):
+    """Mirror of ``LinRegLA_impl(Data, intemps, lNumber)`` (reference src/LinReg_LA.cpp:45-111)."""
+    flat, n_obs = _la_data(Data)
+    N = int(lNumber)
+    t = _f64(intemps)
+    L = t.size
+    th = np.empty(L * 3 * N); ll = np.empty(L * N); lp = np.empty(L * N); w = np.empty(L * N)
+    ess, nc = np.empty(L), np.empty(4)
+    z, u = _f64(noise), _f64(uniforms)
+    _check(lib().smcb200_LinRegLA(_dp(flat), n_obs, _dp(t), L, N, seed, _dp(z), 0 if z is None else z.size, _dp(u), 0 if u is None else u.size,
+                                  _dp(th), _dp(ll), _dp(lp), _dp(w), _dp(ess), _dp(nc)))
+    return {"theta": th.reshape(L, 3, N).transpose(2, 1, 0), "loglike": ll.reshape(L, N).T, "logprior": lp.reshape(L, N).T,
+            "Weights": w.reshape(L, N).T, "ESS": ess, "logNC_standard": nc[0], "logNC_ps_rect": nc[1], "logNC_ps_trap": nc[2],
+            "logNC_ps_trap2": nc[3]}
 
 
 class PfNonlinBS:

@@ -102,6 +102,11 @@ def main():
         k += 1
     out["ncases"] = np.array(k)
     np.savez_compressed(os.path.join(HERE, "pflineart_kat.npz"), **out)
+    # ---- 5. the radiata data set (42 x 3: y, x1, x2), bundled data of the reference (inst/rawdata/radiata-data.csv)
+    ref_dir = os.environ.get("SMC_REF_DIR", "/root/reference")
+    raw = np.loadtxt(os.path.join(ref_dir, "inst", "rawdata", "radiata-data.csv"), skiprows=1)
+    assert raw.shape == (42, 3)
+    np.savez(os.path.join(HERE, "radiata.npz"), data=raw)
     print("golden fixtures written to", HERE)
 
 

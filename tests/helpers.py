@@ -239,3 +239,28 @@ def r_pflineart(data, N, mode, threshold, z, U):
                            dp(out["logNC"]), dp(out["ESS"]), rs.ctypes.data_as(IP))
     out["resampled"] = rs
     return out
+
+
+# ---- LinRegLA / LinRegLA_adapt --------------------------------------------------------------------------------
+def radiata():
+    """The 42-observation radiata pine data (y, x1, x2): fixture extracted from the reference's bundled data file by
+    tests/golden/make_golden.py (reference inst/rawdata/radiata-data.csv)."""
+    return np.load(os.path.join(GOLDEN, "radiata.npz"))["data"]
+
+
+def o_linreg_la(Data, N, adaptive=True, temps=None, resampTol=0.5, tempTol=0.9, z=None, U=None, seed=0, max_temps=512):
+    d = np.asarray(Data, dtype=np.float64)
+    flat = np.ascontiguousarray(d.T.reshape(-1)); n_obs = d.shape[0]
+    th = np.empty(max_temps * 3 * N); ll = np.empty(max_temps * N); lp = np.empty(max_temps * N); w = np.empty(max_temps * N)
+    ess, tt, reps, acc = (np.empty(max_temps) for _ in range(4))
+    nc = np.empty(4)
+    z = None if z is None else f64(z); U = None if U is None else f64(U)
+    tin = None if temps is None else f64(temps)
+    o = oracle(); o.smco_linreg_la.restype = L
+    Lr = o.smco_linreg_la(dp(flat), L(n_obs), L(N), 1 if adaptive else 0, dp(tin), L(0 if tin is None else tin.size), D(resampTol), D(tempTol),
+                          dp(z), dp(U), ctypes.c_ulonglong(seed), L(max_temps), dp(th), dp(ll), dp(lp), dp(w), dp(ess), dp(tt), dp(reps), dp(nc), dp(acc))
+    assert Lr > 0
+    return {"theta": th[:Lr * 3 * N].reshape(Lr, 3, N).transpose(2, 1, 0), "loglike": ll[:Lr * N].reshape(Lr, N).T,
+            "logprior": lp[:Lr * N].reshape(Lr, N).T, "Weights": w[:Lr * N].reshape(Lr, N).T, "ESS": ess[:Lr].copy(), "Temps": tt[:Lr].copy(),
+            "mcmcRepeats": reps[:Lr].copy(), "logNC_standard": nc[0], "logNC_ps_rect": nc[1], "logNC_ps_trap": nc[2], "logNC_ps_trap2": nc[3],
+            "acceptProb": acc[:Lr].copy()}
