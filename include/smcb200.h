@@ -148,6 +148,25 @@ int smcb200_LinRegLA(const double* data_host, long n_obs, const double* temps_ho
                      const double* noise_host, long n_noise, const double* uniforms_host, long n_uniforms, double* theta_host,
                      double* loglike_host, double* logprior_host, double* weights_host, double* ess_host, double* lognc4_host);
 
+/* ---- model level: nonLinPMMH (reference src/nonLinPMMH.cpp:37-153, R/nonLinPMMH.R) ------------------------------------ */
+
+/* Progress hook: the reference prints to Rcpp::Rcout every msg_freq iterations (:116-138); same quantities. */
+typedef void (*smcb200_pmmh_progress)(long iteration, long iterations, double mean_sigv, double mean_sigw, double loglike,
+                                      double logprior, double acceptance_rate, void* user);
+
+/* Particle-marginal Metropolis-Hastings: `iterations` random-walk proposals on (sigv, sigw) starting at (10, 10); each
+ * evaluates the likelihood with a `particles`-particle bootstrap filter over data[0..T).  Reference behaviour:
+ * resample_mode = SMCB200_MULTINOMIAL, threshold = 0.5 (:77).  Outputs have iterations+1 entries, as the reference's
+ * DataFrame(samples_sigv, samples_sigw, loglike, logprior, MH_acceptance_rate).
+ * Optional injected draws: innov_v/innov_w/unif [iterations] (the pre-drawn outer-chain randomness, :72-74, already scaled:
+ * 0.15 z, 0.08 z); filter_noise [(iterations+1) * particles * T] and filter_unif [(iterations+1) * per-filter count] for the
+ * inner filters (layouts as in smcb200_pfNonlinBS).  Independent chains are independent calls (one per GPU). */
+int smcb200_nonLinPMMH(const double* data_host, long T, long particles, long iterations, uint64_t seed, int resample_mode,
+                       double threshold, const double* innov_v_host, const double* innov_w_host, const double* unif_host,
+                       const double* filter_noise_host, const double* filter_unif_host, smcb200_pmmh_progress progress,
+                       long msg_freq, void* user, double* samples_sigv_host, double* samples_sigw_host, double* loglike_host,
+                       double* logprior_host, double* accept_rate_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -362,6 +362,8 @@ template <class T> struct Vector_ {
     Vector_(int n) : v(n) {}
     Vector_(unsigned long n) : v(n) {}
     Vector_(const std::vector<T>& o) : v(o) {}
+    Vector_(long n, T fill) : v(n, fill) {}
+    Vector_(unsigned long n, T fill) : v(n, fill) {}
     template <class U> Vector_(const arma::Col<U>& o) : v(o.d.begin(), o.d.end()) {}
     T& operator()(long i) { return v[i]; }
     const T& operator()(long i) const { return v[i]; }

@@ -41,6 +41,11 @@ long smco_linreg_la(const double* data, long n_obs, long N, int adaptive, const 
                     double tempTol, const double* z, const double* U, unsigned long long seed, long max_temps, double* theta_out,
                     double* ll_out, double* lp_out, double* w_out, double* ess_out, double* temps_out, double* reps_out,
                     double* lognc_out, double* accept_out);
+double smco_pmmh_filter(const double* y, long T, long N, double sigv, double sigw, int mode, double threshold, const double* z,
+                        const double* U, unsigned long long seed);
+int smco_nonlin_pmmh(const double* y, long T, long N, long M, int mode, double threshold, const double* innov_v, const double* innov_w,
+                     const double* unif, const double* filter_noise, const double* filter_unif, unsigned long long seed, double* sigv,
+                     double* sigw, double* loglike, double* logprior, double* accept_rate);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 

@@ -56,6 +56,9 @@ def lib():
                                          _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, ctypes.c_long] + [_c_double_p] * 9
     L.smcb200_LinRegLA.argtypes = [_c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_uint64,
                                    _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long] + [_c_double_p] * 6
+    L.smcb200_nonLinPMMH.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_int, ctypes.c_double,
+                                     _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, ctypes.c_void_p, ctypes.c_long,
+                                     ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
@@ -234,6 +237,35 @@ def LinRegLA(Data, intemps, lNumber, seed=1, noise=None, uniforms=None):
     return {"theta": th.reshape(L, 3, N).transpose(2, 1, 0), "loglike": ll.reshape(L, N).T, "logprior": lp.reshape(L, N).T,
             "Weights": w.reshape(L, N).T, "ESS": ess, "logNC_standard": nc[0], "logNC_ps_rect": nc[1], "logNC_ps_trap": nc[2],
             "logNC_ps_trap2": nc[3]}
+
+
+_PMMH_CB = ctypes.CFUNCTYPE(None, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                            ctypes.c_double, ctypes.c_void_p)
+
+
+def nonLinPMMH(data, lNumber, lMCMCits, verbose=False, msg_freq=100, resample_mode=MULTINOMIAL, threshold=0.5, seed=1, innovations=None,
+               filter_noise=None, filter_uniforms=None, progress=None):
+    """Mirror of ``nonLinPMMH_impl(data, lNumber, lMCMCits, verbose, msg_freq)`` (reference src/nonLinPMMH.cpp:37-153): dict with
+    samples_sigv, samples_sigw, loglike, logprior, MH_acceptance_rate (lMCMCits + 1 entries each).
+    ``innovations`` = (innov_v, innov_w, unif) pre-drawn outer-chain randomness; filter_* inject the inner filters' draws."""
+    y = _f64(np.asarray(data).reshape(-1))
+    M = int(lMCMCits)
+    out = [np.empty(M + 1) for _ in range(5)]
+    iv = iw = uu = None
+    if innovations is not None:
+        iv, iw, uu = (_f64(a) for a in innovations)
+    zn, un = _f64(filter_noise), _f64(filter_uniforms)
+    cb = None
+    if progress is not None or verbose:
+        def _cb(i, m, mv, mw, ll, lp, ar, _user):
+            if progress is not None:
+                progress(i, m, mv, mw, ll, lp, ar)
+            else:
+                print(f"Percentage completed: {round(100.0 * i / m)}%. mean sigv {mv:.4f} mean sigw {mw:.4f} loglike {ll:.3f} acceptance {round(100 * ar)}%")
+        cb = _PMMH_CB(_cb)
+    _check(lib().smcb200_nonLinPMMH(_dp(y), y.size, int(lNumber), M, seed, resample_mode, threshold, _dp(iv), _dp(iw), _dp(uu), _dp(zn), _dp(un),
+                                    ctypes.cast(cb, ctypes.c_void_p) if cb else None, msg_freq, None, *[_dp(o) for o in out]))
+    return dict(zip(("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"), out))
 
 
 class PfNonlinBS:

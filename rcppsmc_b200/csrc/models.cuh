@@ -106,4 +106,41 @@ struct Lineart {
     }
 };
 
+
+// Inner bootstrap filter of the particle-marginal Metropolis-Hastings example: reference src/nonLinPMMH.cpp:155-190.
+// Same nonlinear model as NonlinBS with (sigv, sigw) as parameters, x0 ~ N(0, 5), cos(1.2 (t+1)) and fully normalised
+// Gaussian log-weights (R::dnorm(..., log = TRUE)).  Only the log normalising constant is needed by the outer chain.
+struct NonlinPMMH {
+    static constexpr int D = 1;
+    static constexpr int NZ_INIT = 1;
+    static constexpr int NZ_MOVE = 1;
+    static constexpr int NSHIFT = 0;
+    static constexpr int NOBS = 0;
+    struct Params {
+        const double* y;
+        const double* cterm;   // 8 cos(1.2 (t + 1)) for t = 0..T-1, tabulated on the host
+        double sigv, sigw;
+        double log_sigw;       // log(sigw) from the host (NaN for a negative proposal: the chain then rejects)
+    };
+    __device__ static __forceinline__ double dnorm_log(double x, double mu, const Params& p) {  // R nmath dnorm4, give_log
+        const double ln_sqrt_2pi = 0.918938533204672741780329736406;
+        double z = (x - mu) / p.sigw;
+        return -(ln_sqrt_2pi + 0.5 * z * z + p.log_sigw);
+    }
+    __device__ static __forceinline__ void init(double (&x)[D], double& lw, const Params& p, const double* z) {  // :168-173
+        const double sd0 = 2.23606797749979;  // sqrt(5.0)
+        x[0] = 0.0 + sd0 * z[0];
+        lw = dnorm_log(p.y[0], (x[0] * x[0]) / 20.0, p);
+    }
+    __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {  // :181-186
+        double v = x[0];
+        v = v / 2.0 + 25.0 * v / (1 + v * v) + p.cterm[t] + (0.0 + p.sigv * z[0]);
+        x[0] = v;
+        lw += dnorm_log(p.y[t], (v * v) / 20.0, p);
+    }
+    __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[1]) { h[0] = 0.0; }
+    __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[1]) { f[0] = 0.0; }
+    __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
+};
+
 }  // namespace smcb

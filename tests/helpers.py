@@ -264,3 +264,31 @@ def o_linreg_la(Data, N, adaptive=True, temps=None, resampTol=0.5, tempTol=0.9, 
             "logprior": lp[:Lr * N].reshape(Lr, N).T, "Weights": w[:Lr * N].reshape(Lr, N).T, "ESS": ess[:Lr].copy(), "Temps": tt[:Lr].copy(),
             "mcmcRepeats": reps[:Lr].copy(), "logNC_standard": nc[0], "logNC_ps_rect": nc[1], "logNC_ps_trap": nc[2], "logNC_ps_trap2": nc[3],
             "acceptProb": acc[:Lr].copy()}
+
+
+# ---- nonLinPMMH -----------------------------------------------------------------------------------------------------
+def o_pmmh_filter(y, N, sigv, sigw, mode, threshold, z=None, U=None, seed=0):
+    y = f64(y)
+    o = oracle(); o.smco_pmmh_filter.restype = D
+    return o.smco_pmmh_filter(dp(y), L(y.size), L(N), D(sigv), D(sigw), mode, D(threshold), dp(None if z is None else f64(z)),
+                              dp(None if U is None else f64(U)), ctypes.c_ulonglong(seed))
+
+
+def o_pmmh(y, N, M, mode, threshold, innov, filter_noise=None, filter_unif=None, seed=0):
+    y = f64(y)
+    out = [np.empty(M + 1) for _ in range(5)]
+    iv, iw, uu = (f64(a) for a in innov)
+    rc = oracle().smco_nonlin_pmmh(dp(y), L(y.size), L(N), L(M), mode, D(threshold), dp(iv), dp(iw), dp(uu),
+                                   dp(None if filter_noise is None else f64(filter_noise)), dp(None if filter_unif is None else f64(filter_unif)),
+                                   ctypes.c_ulonglong(seed), *[dp(o) for o in out])
+    assert rc == 0
+    return dict(zip(("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"), out))
+
+
+def r_pmmh(y, N, M, seed):
+    y = f64(y)
+    r_clear(); ref().smcref_seed(ctypes.c_uint64(seed))
+    out = [np.empty(M + 1) for _ in range(5)]
+    rc = ref().smcref_nonlin_pmmh(dp(y), L(y.size), L(N), L(M), *[dp(o) for o in out])
+    assert rc == 0
+    return dict(zip(("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"), out))
