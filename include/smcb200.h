@@ -167,6 +167,14 @@ int smcb200_nonLinPMMH(const double* data_host, long T, long particles, long ite
                        long msg_freq, void* user, double* samples_sigv_host, double* samples_sigw_host, double* loglike_host,
                        double* logprior_host, double* accept_rate_host);
 
+/* LinReg_impl (reference src/LinReg.cpp:46-84): data-annealing SMC sampler, one observation per step, MULTINOMIAL / 0.5,
+ * 10 random-walk MH repeats per step.  Outputs: theta [N x 3] column-major, weights [N] (normalised), logNC.
+ * Injected draws: noise / uniforms as in smcb200_LinRegLA (Initialise 2 normals + 3 uniforms per particle, then per
+ * repeat and particle 3 normals + 1 uniform); resample_uniforms [n_obs * N] indexed by step for the multinomial draws. */
+int smcb200_LinReg(const double* data_host, long n_obs, long particles, uint64_t seed, const double* noise_host, long n_noise,
+                   const double* uniforms_host, long n_uniforms, const double* resample_uniforms_host, double* theta_host,
+                   double* weights_host, double* lognc_host);
+
 #ifdef __cplusplus
 }
 #endif

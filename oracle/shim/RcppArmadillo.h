@@ -108,6 +108,7 @@ template <class T> struct Col {
     const T* end() const { return d.data() + d.size(); }
     Col head(uword n) const { Col r(n); std::copy(d.begin(), d.begin() + n, r.d.begin()); return r; }
     Col tail(uword n) const { Col r(n); std::copy(d.end() - n, d.end(), r.d.begin()); return r; }
+    Col rows(uword a, uword b) const { return subvec(a, b); }
     Col subvec(uword a, uword b) const { Col r(b - a + 1); std::copy(d.begin() + a, d.begin() + b + 1, r.d.begin()); return r; }
     template <class U> Col elem(const Col<U>& ix) const {
         Col r(ix.d.size());

@@ -46,6 +46,8 @@ double smco_pmmh_filter(const double* y, long T, long N, double sigv, double sig
 int smco_nonlin_pmmh(const double* y, long T, long N, long M, int mode, double threshold, const double* innov_v, const double* innov_w,
                      const double* unif, const double* filter_noise, const double* filter_unif, unsigned long long seed, double* sigv,
                      double* sigw, double* loglike, double* logprior, double* accept_rate);
+int smco_linreg(const double* data, long n_obs, long N, const double* z, const double* U, const double* Udraw,
+                unsigned long long seed, double* theta_out, double* w_out, double* lognc_out);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 

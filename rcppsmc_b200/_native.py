@@ -59,6 +59,8 @@ def lib():
     L.smcb200_nonLinPMMH.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_int, ctypes.c_double,
                                      _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, ctypes.c_void_p, ctypes.c_long,
                                      ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]
+    L.smcb200_LinReg.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long,
+                                 _c_double_p, _c_double_p, _c_double_p, _c_double_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
@@ -200,6 +202,17 @@ def _la_data(Data):
     if d.ndim != 2 or d.shape[1] != 2:
         raise ValueError("Data must be [n_obs x 2] (y, x)")
     return np.ascontiguousarray(d.T.reshape(-1)), d.shape[0]   # column-major: y column then x column
+
+
+def LinReg(Data, lNumber, seed=1, noise=None, uniforms=None, resample_uniforms=None):
+    """Mirror of ``LinReg_impl(Data, lNumber)`` (reference src/LinReg.cpp:46-84): dict(theta [N,3], weights [N], logNC)."""
+    flat, n_obs = _la_data(Data)
+    N = int(lNumber)
+    th, w, nc = np.empty(3 * N), np.empty(N), np.empty(1)
+    z, u, ud = _f64(noise), _f64(uniforms), _f64(resample_uniforms)
+    _check(lib().smcb200_LinReg(_dp(flat), n_obs, N, seed, _dp(z), 0 if z is None else z.size, _dp(u), 0 if u is None else u.size, _dp(ud),
+                                _dp(th), _dp(w), _dp(nc)))
+    return {"theta": th.reshape(3, N).T, "weights": w, "logNC": float(nc[0])}
 
 
 def LinRegLA_adapt(Data, lNumber, resampTol=0.5, tempTol=0.9, seed=1, noise=None, uniforms=None, max_temps=512):

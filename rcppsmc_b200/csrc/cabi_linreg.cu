@@ -79,7 +79,7 @@ long run_la(bool adaptive, const double* data_host, long n_obs, const double* te
     a.hist.lcap = lcap;
     a.am = AncestorMap{zmask.as<uint32_t>(), zbase.as<uint32_t>(), surplus.as<uint32_t>()};
     a.partial = partial.as<double>(); a.seed = seed; a.zin = zin.as<double>(); a.uin = uin.as<double>();
-    a.adaptive = adaptive ? 1 : 0; a.rho_n = tempTol * (double)n;
+    a.adaptive = adaptive ? 1 : 0; a.data_annealing = 0; a.rho_n = tempTol * (double)n;
 
     LaCtrl h{};
     h.T = 0; h.temp_prev = 0.0; h.temp_cur = adaptive ? 0.0 : temps_in[0];
@@ -171,7 +171,108 @@ long run_la(bool adaptive, const double* data_host, long n_obs, const double* te
     return L;
 }
 
+// LinReg_impl (src/LinReg.cpp:46-84): data annealing, MULTINOMIAL / 0.5, 10 random-walk MH repeats per step with chol(covRW).
+void run_linreg(const double* data_host, long n_obs, long particles, uint64_t seed, const double* noise_host, long n_noise,
+                const double* unif_host, long n_unif, const double* draw_unif_host, double* theta, double* weights, double* lognc) {
+    if (!data_host || n_obs < 1 || particles < 1 || particles > 2147483647L) throw std::invalid_argument("LinReg: data, n_obs >= 1 and 1 <= particles < 2^31 required");
+    if ((noise_host == nullptr) != (unif_host == nullptr)) throw std::invalid_argument("LinReg: inject both noise and uniforms or neither");
+    require_device();
+    const long long n = particles;
+    cudaStream_t st = 0;
+    std::vector<double> y(data_host, data_host + n_obs), xc(n_obs);
+    {
+        double s0 = 0, s1 = 0; long i, j;
+        const double* x = data_host + n_obs;
+        for (i = 0, j = 1; j < n_obs; i += 2, j += 2) { s0 += x[i]; s1 += x[j]; }
+        if (i < n_obs) s0 += x[i];
+        const double mean_x = (s0 + s1) / (double)n_obs;
+        for (long k = 0; k < n_obs; ++k) xc[k] = x[k] - mean_x;
+    }
+    DevBuf d_y(sizeof(double) * n_obs), d_xc(sizeof(double) * n_obs);
+    SMCB_CUDA(cudaMemcpy(d_y.p, y.data(), sizeof(double) * n_obs, cudaMemcpyHostToDevice));
+    SMCB_CUDA(cudaMemcpy(d_xc.p, xc.data(), sizeof(double) * n_obs, cudaMemcpyHostToDevice));
+    DevBuf state(sizeof(double) * 10 * n), lw(sizeof(double) * n), hs(sizeof(double) * 8);
+    const long long ntiles = scan_tiles(n);
+    DevBuf zmask(sizeof(uint32_t) * ((n + 31) / 32 + 64)), zbase(sizeof(uint32_t) * ((n + 31) / 32 + 64)), surplus(sizeof(uint32_t) * n);
+    DevBuf status(sizeof(unsigned long long) * 3 * ntiles), ctrl(sizeof(LaCtrl)), cum(sizeof(unsigned long long) * n), count(sizeof(int) * n);
+    DevBuf extra(sizeof(unsigned long long) * 2), step(sizeof(long long));
+    int dev = 0, sms = 0;
+    SMCB_CUDA(cudaGetDevice(&dev));
+    SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long want = (n + 255) / 256;
+    const int grid = (int)(want < 2LL * sms ? want : 2LL * sms);
+    const int grid_mcmc = (int)((n + 127) / 128 < 8LL * sms ? (n + 127) / 128 : 8LL * sms);
+    DevBuf partial(sizeof(double) * 16 * (size_t)(grid_mcmc > grid ? grid_mcmc : grid));
+    DevBuf zin, uin, udraw;
+    if (noise_host) {
+        zin = DevBuf(sizeof(double) * n_noise); uin = DevBuf(sizeof(double) * n_unif);
+        SMCB_CUDA(cudaMemcpy(zin.p, noise_host, sizeof(double) * n_noise, cudaMemcpyHostToDevice));
+        SMCB_CUDA(cudaMemcpy(uin.p, unif_host, sizeof(double) * n_unif, cudaMemcpyHostToDevice));
+    }
+    if (draw_unif_host) {   // resampling uniforms, indexed by step: U[t * N + j]
+        udraw = DevBuf(sizeof(double) * (size_t)n_obs * n);
+        SMCB_CUDA(cudaMemcpy(udraw.p, draw_unif_host, sizeof(double) * (size_t)n_obs * n, cudaMemcpyHostToDevice));
+    }
+    LaArgs a{};
+    for (int k = 0; k < 5; ++k) { a.buf.a[k] = state.as<double>() + (size_t)k * n; a.buf.b[k] = state.as<double>() + (size_t)(5 + k) * n; }
+    a.buf.lw = lw.as<double>(); a.buf.n = n;
+    a.data = LaData{d_y.as<double>(), d_xc.as<double>(), (int)n_obs};
+    a.ctrl = ctrl.as<LaCtrl>();
+    a.hist.lcap = 0;
+    a.am = AncestorMap{zmask.as<uint32_t>(), zbase.as<uint32_t>(), surplus.as<uint32_t>()};
+    a.partial = partial.as<double>(); a.seed = seed; a.zin = zin.as<double>(); a.uin = uin.as<double>();
+    a.adaptive = 0; a.data_annealing = 1; a.rho_n = 0.0;
+    LaCtrl h{};
+    h.thr = 0.5 * (double)n; h.log_n = std::log((double)n); h.accept_prob = -1.0; h.n_repeats = 10;   // LinReg.cpp:62-63
+    {
+        const double A[9] = {2500, -2.5, 0.03, -2.5, 130.0, 0.0, 0.03, 0.0, 0.04};   // covRW, LinReg.cpp:34-35
+        double* U = h.chol;
+        for (int k = 0; k < 9; ++k) U[k] = 0.0;
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i <= j; ++i) {
+                double s = A[i + 3 * j];
+                for (int k = 0; k < i; ++k) s -= U[k + 3 * i] * U[k + 3 * j];
+                U[i + 3 * j] = (i == j) ? std::sqrt(s) : s / U[i + 3 * i];
+            }
+    }
+    SMCB_CUDA(cudaMemcpy(ctrl.p, &h, sizeof h, cudaMemcpyHostToDevice));
+    ScanWs ws{status.as<unsigned long long>(), status.as<unsigned long long>() + ntiles, status.as<unsigned long long>() + 2 * ntiles};
+    DrawWs dw{cum.as<unsigned long long>(), count.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1)};
+    for (long g = 0; g < n_obs; ++g) {
+        if (g == 0) k_la_init<<<grid, 256, 0, st>>>(a);
+        else k_la_reweight<<<grid, 256, 0, st>>>(a);
+        k_la_pre_resample<<<1, 1, 0, st>>>(a);
+        SMCB_CUDA(cudaMemsetAsync(status.p, 0, sizeof(unsigned long long) * 3 * ntiles, st));
+        SMCB_CUDA(cudaMemsetAsync(extra.p, 0, sizeof(unsigned long long) * 2, st));
+        launch_resample_draws<SRC_LOGW>(MULTINOMIAL, a.buf.lw, n, &a.ctrl->lse, &a.ctrl->resampled, udraw.as<double>(), &a.ctrl->T, seed,
+                                        &a.ctrl->ticket, ws, dw, a.am, nullptr, st);
+        k_la_mcmc<<<grid_mcmc, 128, 0, st>>>(a);
+        SMCB_CUDA(cudaGetLastError());
+    }
+    SMCB_CUDA(cudaStreamSynchronize(st));
+    SMCB_CUDA(cudaMemcpy(&h, ctrl.p, sizeof h, cudaMemcpyDeviceToHost));
+    double* const* cur = h.parity ? a.buf.b : a.buf.a;
+    for (int cidx = 0; cidx < 3; ++cidx)
+        if (theta) SMCB_CUDA(cudaMemcpy(theta + (size_t)cidx * n, cur[cidx], sizeof(double) * n, cudaMemcpyDeviceToHost));   // arma::mat [N x 3]
+    if (weights) {
+        std::vector<double> lwh(n);
+        SMCB_CUDA(cudaMemcpy(lwh.data(), a.buf.lw, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < n; ++i) weights[i] = std::exp(lwh[i] - h.lse);   // GetParticleWeight()
+    }
+    if (lognc) *lognc = h.path;
+}
+
 }  // namespace
+
+extern "C" int smcb200_LinReg(const double* data_host, long n_obs, long particles, uint64_t seed, const double* noise_host, long n_noise,
+                              const double* uniforms_host, long n_uniforms, const double* resample_uniforms_host, double* theta_host,
+                              double* weights_host, double* lognc_host) {
+    return guarded([&]() -> int {
+        run_linreg(data_host, n_obs, particles, seed, noise_host, n_noise, uniforms_host, n_uniforms, resample_uniforms_host, theta_host,
+                   weights_host, lognc_host);
+        return SMCB200_OK;
+    });
+}
 
 extern "C" long smcb200_LinRegLA_adapt(const double* data_host, long n_obs, long particles, double resampTol, double tempTol,
                                        uint64_t seed, const double* noise_host, long n_noise, const double* uniforms_host, long n_uniforms,

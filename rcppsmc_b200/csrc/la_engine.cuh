@@ -87,6 +87,19 @@ __device__ __forceinline__ double la_logprior(const double th[3]) {
            - inv_b / exp(th[2]) - th[2] * (a_prior + 1.0);
 }
 
+// Data annealing (src/LinReg.cpp:87-118): weight of observation t, and the log posterior given observations 0..t.
+__device__ __forceinline__ double lr_logweight(int t, const double th[3], const LaData& d) {
+    const double mean_reg = th[0] + th[1] * d.xc[t];
+    const double sigma = sqrt(exp(th[2]));
+    const double r = d.y[t] - mean_reg;
+    return -log(sigma) - (r * r) / (2.0 * sigma * sigma) - 0.5 * log(2.0 * 3.14159265358979323846);
+}
+__device__ __forceinline__ double lr_logposterior(int t, const double th[3], const LaData& d) {
+    LaData part = d;
+    part.n_obs = t + 1;
+    return la_loglik(th, part) + la_logprior(th);   // log_normpdf + log_prior (:117)
+}
+
 // Block partials -> last block: generic helper for the small reductions of this file.
 template <int NV>
 __device__ __forceinline__ bool la_block_to_grid(const double (&v)[NV], double* partial, unsigned int* done, double (&tot)[NV]) {
@@ -179,6 +192,7 @@ struct LaArgs {
     const double* zin;           // injected standard normals (reference consumption order) or null
     const double* uin;           // injected uniforms or null
     int adaptive;                // 1: LinRegLA_adapt, 0: LinRegLA (fixed schedule / proposal / repeats)
+    int data_annealing;          // 1: LinReg (src/LinReg.cpp): one observation per step, MH target = prior x likelihood(0..t)
     double rho_n;                // target conditional ESS (tempTol * N)
 };
 
@@ -206,7 +220,7 @@ static __global__ void __launch_bounds__(256) k_la_init(LaArgs a) {
         for (int k = 0; k < 3; ++k) g += -log(u[k]);                 // Gamma(3, 1) as a sum of exponentials
         th[2] = log(1.0 / (b_prior * g));
         const double ll = la_loglik(th, a.data), lp = la_logprior(th);
-        const double lw = temp0 * ll - log_n;                        // logweight = temp(0) loglike; sampler.h:495
+        const double lw = (a.data_annealing ? lr_logweight(0, th, a.data) : temp0 * ll) - log_n;   // pfInitialise weight; sampler.h:495
         a.buf.a[0][i] = th[0]; a.buf.a[1][i] = th[1]; a.buf.a[2][i] = th[2]; a.buf.a[3][i] = ll; a.buf.a[4][i] = lp;
         a.buf.lw[i] = lw;
         double h[1] = {ll};
@@ -279,11 +293,15 @@ static __global__ void __launch_bounds__(256) k_la_reweight(LaArgs a) {
     LaCtrl* c = a.ctrl;
     const long long n = a.buf.n;
     const double dt = c->temp_cur - c->temp_prev, lse_prev = c->lse;
-    const double* ll = (c->parity ? a.buf.b : a.buf.a)[3];
+    double* const* cur = c->parity ? a.buf.b : a.buf.a;
+    const double* ll = cur[3];
+    const int tnext = (int)c->T + 1;
     LseAcc<1> acc; acc.clear();
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const double l = ll[i];
-        const double lw = (a.buf.lw[i] - lse_prev) + dt * l;
+        double inc = dt * l;
+        if (a.data_annealing) { double th[3] = {cur[0][i], cur[1][i], cur[2][i]}; inc = lr_logweight(tnext, th, a.data); }   // LinReg.cpp:139
+        const double lw = (a.buf.lw[i] - lse_prev) + inc;
         a.buf.lw[i] = lw;
         double h[1] = {l};
         acc.add(lw, h);
@@ -348,7 +366,7 @@ static __global__ void __launch_bounds__(256) k_la_cov(LaArgs a, int phase, doub
 // resampling uniform + bookkeeping that must precede the resampling pass
 static __global__ void k_la_pre_resample(LaArgs a) {
     LaCtrl* c = a.ctrl;
-    if (c->resampled) {
+    if (c->resampled && !a.data_annealing) {   // LinReg resamples multinomially: its uniforms come from a separate by-step array
         if (a.uin) { c->u_res = a.uin[c->upos]; c->upos += 1; }
         else c->u_res = u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)c->T, ~0ull, 1).a);
     }
@@ -395,6 +413,11 @@ static __global__ void __launch_bounds__(128) k_la_mcmc(LaArgs a) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += U[r + 3 * k] * z[k];
                 pr[r] = th[r] + s;
+            }
+            if (a.data_annealing) {   // LinReg.cpp:150-166: both posteriors are recomputed from the first T+1 observations
+                const double pc = lr_logposterior((int)T, th, a.data), pp = lr_logposterior((int)T, pr, a.data);
+                if (exp(pp - pc) > u) { th[0] = pr[0]; th[1] = pr[1]; th[2] = pr[2]; ++accepted; }
+                continue;
             }
             const double llp = la_loglik(pr, a.data), lpp = la_logprior(pr);
             const double ratio = exp(temp * (llp - ll) + lpp - lp);

@@ -292,3 +292,13 @@ def r_pmmh(y, N, M, seed):
     rc = ref().smcref_nonlin_pmmh(dp(y), L(y.size), L(N), L(M), *[dp(o) for o in out])
     assert rc == 0
     return dict(zip(("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"), out))
+
+
+def o_linreg(Data, N, z=None, U=None, Udraw=None, seed=0):
+    d = np.asarray(Data, dtype=np.float64)
+    flat = np.ascontiguousarray(d.T.reshape(-1)); n_obs = d.shape[0]
+    th, w, nc = np.empty(3 * N), np.empty(N), np.empty(1)
+    rc = oracle().smco_linreg(dp(flat), L(n_obs), L(N), dp(None if z is None else f64(z)), dp(None if U is None else f64(U)),
+                              dp(None if Udraw is None else f64(Udraw)), ctypes.c_ulonglong(seed), dp(th), dp(w), dp(nc))
+    assert rc == 0
+    return {"theta": th.reshape(3, N).T, "weights": w, "logNC": float(nc[0])}

@@ -70,3 +70,24 @@ def test_known_log_evidence_under_native_rng(smc, col, known):
     w = out["Weights"][:, -1]
     alpha = float((w * out["theta"][:, 0, -1]).sum() / w.sum())
     assert 2950 < alpha < 3050
+
+
+def test_data_annealing_sampler_matches_oracle_on_identical_draws(smc):
+    # LinReg_impl: one observation per step, native multinomial resampling, 10 MH repeats per step
+    data = H.radiata()[:, [0, 1]]
+    N = 600
+    rng = np.random.default_rng(21)
+    z, U = rng.standard_normal(2 * N + 3 * N * 10 * 42), rng.random(3 * N + N * 10 * 42)
+    Ud = rng.random(42 * N)
+    exp = H.o_linreg(data, N, z=z, U=U, Udraw=Ud)
+    got = smc.LinReg(data, N, noise=z, uniforms=U, resample_uniforms=Ud)
+    assert abs(got["logNC"] - exp["logNC"]) <= 1e-6 * abs(exp["logNC"])
+    np.testing.assert_allclose(got["theta"], exp["theta"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got["weights"], exp["weights"], rtol=1e-7)
+
+
+def test_data_annealing_known_log_evidence(smc):
+    data = H.radiata()[:, [0, 1]]
+    out = smc.LinReg(data, 1 << 17, seed=4)
+    assert abs(out["logNC"] - (-309.9)) < 0.25       # man/LinReg.Rd:78-80
+    assert abs(out["weights"].sum() - 1.0) < 1e-9
