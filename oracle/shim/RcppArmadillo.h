@@ -110,6 +110,11 @@ template <class T> struct Col {
     Col tail(uword n) const { Col r(n); std::copy(d.end() - n, d.end(), r.d.begin()); return r; }
     Col rows(uword a, uword b) const { return subvec(a, b); }
     Col subvec(uword a, uword b) const { Col r(b - a + 1); std::copy(d.begin() + a, d.begin() + b + 1, r.d.begin()); return r; }
+    struct ElemRef {   // x.elem(indices).fill(v)
+        Col& c; std::vector<uword> ix;
+        void fill(T v) { for (uword i : ix) c.d[i] = v; }
+    };
+    template <class U> ElemRef elem(const Col<U>& ix) { ElemRef r{*this, {}}; for (auto v : ix.d) r.ix.push_back((uword)v); return r; }
     template <class U> Col elem(const Col<U>& ix) const {
         Col r(ix.d.size());
         for (size_t i = 0; i < ix.d.size(); ++i) r.d[i] = d[ix.d[i]];
@@ -178,6 +183,7 @@ template <class T> inline Col<T> cumsum(const Col<T>& a) {
 }
 template <class T> inline double mean(const Col<T>& a) { return (double)sum(a) / (double)a.d.size(); }
 template <class T> inline T as_scalar(const Col<T>& a) { return a.d.at(0); }
+inline double as_scalar(double v) { return v; }
 template <class C> inline C zeros(uword n) { C r(n); std::fill(r.d.begin(), r.d.end(), 0); return r; }
 inline vec zeros(uword n) { return zeros<vec>(n); }
 template <class C> inline C ones(uword n) { C r(n); std::fill(r.d.begin(), r.d.end(), 1); return r; }
@@ -192,6 +198,7 @@ template <class C> struct conv_to {
     template <class U> static C from(const Col<U>& o) { C r(o.d.size()); for (size_t i = 0; i < o.d.size(); ++i) r.d[i] = o.d[i]; return r; }
 };
 // arma::find on a boolean-like column: indices of non-zero entries
+template <class T> inline uvec find(const Col<T>& a, uword k, const char*) { uvec r; for (size_t i = 0; i < a.d.size() && r.d.size() < k; ++i) if (a.d[i]) r.d.push_back(i); r.fix(); return r; }
 template <class T> inline uvec find(const Col<T>& a) { uvec r; for (size_t i = 0; i < a.d.size(); ++i) if (a.d[i]) r.d.push_back(i); r.fix(); return r; }
 #define SHIM_CMP(op)                                                                        \
     template <class T> inline Col<int> operator op(const Col<T>& a, double b) { Col<int> r(a.d.size()); for (size_t i = 0; i < a.d.size(); ++i) r.d[i] = (a.d[i] op b); return r; }
@@ -351,8 +358,12 @@ struct SEXPREC_shim;
 namespace Rcpp {
 inline void stop(const char* m) { throw std::runtime_error(m); }
 inline void stop(const std::string& m) { throw std::runtime_error(m); }
-static std::ostream& Rcout = std::cout;
-static std::ostream& Rcerr = std::cerr;
+// Rcout / Rcerr: private streams that discard their output.  (Not std::cout: inside a Python process a second libstdc++
+// may own the global stream objects, and formatting numbers through them crashes.)
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+inline std::ostream& null_stream() { static NullBuf nb; static std::ostream os(&nb); return os; }
+static std::ostream& Rcout = null_stream();
+static std::ostream& Rcerr = null_stream();
 struct Nil {};
 inline Nil nil() { return Nil{}; }
 
@@ -392,13 +403,22 @@ struct NamedPH {
 inline NamedPH Named(const char* s) { return NamedPH{s}; }
 struct Underscore { NamedPH operator[](const char* s) const { return NamedPH{s}; } };
 static const Underscore _{};
+struct ListSlot;
 struct List {
     std::vector<Column> items; bool is_nil = false;
+    ListSlot operator[](const char* name);
     List() {}
     List(Nil) : is_nil(true) {}
     template <class... A> static List create(A... a) { List l; (l.items.push_back(a), ...); return l; }
     const Column* find(const std::string& n) const { for (auto& c : items) if (c.name == n) return &c; return nullptr; }
 };
+struct ListSlot {   // list["name"] as an rvalue scalar or an assignment target
+    List& l; std::string name;
+    operator double() const { const Column* c = l.find(name); if (!c) throw std::runtime_error("list element missing: " + name); return c->is_scalar ? c->scalar : c->val.at(0); }
+    ListSlot& operator=(const arma::mat& m) { l.items.push_back(Column{name, m.d}); return *this; }
+    ListSlot& operator=(double v) { Column c{name, {v}}; c.scalar = v; c.is_scalar = true; l.items.push_back(c); return *this; }
+};
+inline ListSlot List::operator[](const char* name) { return ListSlot{*this, name}; }
 struct DataFrame : List {
     DataFrame() {}
     DataFrame(Nil n) : List(n) {}
@@ -414,6 +434,21 @@ struct Function {
 };
 inline NumericVector rnorm(long n, double m = 0.0, double s = 1.0) { NumericVector r(n); for (long i = 0; i < n; ++i) r.v[i] = m + s * shim::norm01(); return r; }
 inline NumericVector runif(long n, double a = 0.0, double b = 1.0) { NumericVector r(n); for (long i = 0; i < n; ++i) r.v[i] = a + (b - a) * shim::unif01(); return r; }
+template <class T> inline Vector_<T> operator-(const Vector_<T>& a, int b) { Vector_<T> r(a); for (auto& v : r.v) v -= b; return r; }
+inline NumericVector wrap(const arma::vec& x) { return NumericVector(x.d); }
+// Rcpp::sample(n, size, replace, probs): 1-based draws by sequential inverse CDF on the normalised probabilities, one
+// unif_rand() per draw.  (R sorts the probabilities first and switches to Walker's alias method for n >= 200; this
+// stand-in keeps the natural order -- same distribution, parity-unpinned like the rest of the RNG surface.)
+inline IntegerVector sample(int n, int size, bool /*replace*/, const NumericVector& probs) {
+    double tot = 0.0; for (int i = 0; i < n; ++i) tot += probs.v[i];
+    IntegerVector r(size);
+    for (int s = 0; s < size; ++s) {
+        double u = shim::unif01(), c = 0.0; int j = 0;
+        for (; j < n - 1; ++j) { c += probs.v[j] / tot; if (u <= c) break; }
+        r.v[s] = j + 1;
+    }
+    return r;
+}
 template <class T> inline T as(const NumericVector& x);
 template <> inline arma::vec as<arma::vec>(const NumericVector& x) { return arma::vec(x.v); }
 template <> inline NumericVector as<NumericVector>(const NumericVector& x) { return x; }
