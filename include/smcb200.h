@@ -175,6 +175,21 @@ int smcb200_LinReg(const double* data_host, long n_obs, long particles, uint64_t
                    const double* uniforms_host, long n_uniforms, const double* resample_uniforms_host, double* theta_host,
                    double* weights_host, double* lognc_host);
 
+/* ---- model level: blockpfGaussianOpt (reference src/blockpfgaussianopt.cpp:41-71, R/blockpfGaussianOpt.R) ------------- */
+
+/* Block-sampling particle filter with the optimal Gaussian block proposal; each particle is a whole path.
+ * SYSTEMATIC resampling at ESS < particles/2 (:53).  Outputs mirror List(weight, values, logNC) (:70):
+ * weight_host [particles] = GetParticleWeight() (normalised), values_host [particles x n_data] column-major (row i is the
+ * path of particle i), lognc_host [1].  Optional diagnostics: ess_host [n_data] (ESS seen by each step's resampling
+ * decision), resampled_host [n_data], ancestors_host [n_data][particles] (uRSIndices of each step, identity rows when the
+ * step did not resample).
+ * Optional injected draws: noise_host [n_data][lag][particles] standard normals, entry (t, k, i) is the k-th draw of
+ * particle i's move at time t (k = 0 samples value[t], k >= 1 the backward draws in the reference's order, :121-127);
+ * uniforms_host [n_data] systematic base uniforms by step.  NULL -> Philox(seed). */
+int smcb200_blockpfGaussianOpt(const double* data_host, long n_data, long particles, long lag, uint64_t seed,
+                               const double* noise_host, const double* uniforms_host, double* weight_host, double* values_host,
+                               double* lognc_host, double* ess_host, int* resampled_host, uint32_t* ancestors_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ int smco_nonlin_pmmh(const double* y, long T, long N, long M, int mode, double t
                      double* sigw, double* loglike, double* logprior, double* accept_rate);
 int smco_linreg(const double* data, long n_obs, long N, const double* z, const double* U, const double* Udraw,
                 unsigned long long seed, double* theta_out, double* w_out, double* lognc_out);
+int smco_blockpf(const double* y, long T, long N, long lag_max, const double* z, const double* U, unsigned long long seed,
+                 double* weight, double* values, double* lognc, double* ess_trace, int* resampled, unsigned* anc);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 

@@ -61,6 +61,8 @@ def lib():
                                      ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]
     L.smcb200_LinReg.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long,
                                  _c_double_p, _c_double_p, _c_double_p, _c_double_p]
+    L.smcb200_blockpfGaussianOpt.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, _c_double_p,
+                                             _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_uint_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
@@ -279,6 +281,28 @@ def nonLinPMMH(data, lNumber, lMCMCits, verbose=False, msg_freq=100, resample_mo
     _check(lib().smcb200_nonLinPMMH(_dp(y), y.size, int(lNumber), M, seed, resample_mode, threshold, _dp(iv), _dp(iw), _dp(uu), _dp(zn), _dp(un),
                                     ctypes.cast(cb, ctypes.c_void_p) if cb else None, msg_freq, None, *[_dp(o) for o in out]))
     return dict(zip(("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"), out))
+
+
+def blockpfGaussianOpt(data, particles, lag, seed=1, noise=None, uniforms=None, diagnostics=False):
+    """Mirror of ``blockpfGaussianOpt_impl(data, part, lag)`` (reference src/blockpfgaussianopt.cpp:41-71): dict with weight [N],
+    values [N x T] and logNC.  ``noise`` [T][lag][N] / ``uniforms`` [T] inject the draws; ``diagnostics`` adds the per-step ESS,
+    resampling flags and ancestor rows [T][N]."""
+    y = _f64(np.asarray(data).reshape(-1))
+    T, N = y.size, int(particles)
+    w, v, nc = np.empty(N), np.empty((T, N)), np.empty(1)
+    zn, un = _f64(noise), _f64(uniforms)
+    if zn is not None and zn.size != T * int(lag) * N:
+        raise ValueError("noise must have T * lag * particles entries")
+    ess = rs = anc = None
+    if diagnostics:
+        ess, rs, anc = np.empty(T), np.empty(T, dtype=np.int32), np.empty((T, N), dtype=np.uint32)
+    _check(lib().smcb200_blockpfGaussianOpt(_dp(y), T, N, int(lag), seed, _dp(zn), _dp(un), _dp(w), _dp(v), _dp(nc), _dp(ess),
+                                            rs.ctypes.data_as(_c_int_p) if rs is not None else None,
+                                            anc.ctypes.data_as(_c_uint_p) if anc is not None else None))
+    out = {"weight": w, "values": v.T, "logNC": float(nc[0])}
+    if diagnostics:
+        out.update(ESS=ess, resampled=rs, ancestors=anc)
+    return out
 
 
 class PfNonlinBS:

@@ -16,8 +16,33 @@ sys.path.insert(0, os.path.dirname(HERE))
 import helpers as H  # noqa: E402
 
 
+def blockpf_fixture():
+    """blockpfGaussianOpt_impl outputs of the compiled reference on injected draws (src/blockpfgaussianopt.cpp:41-71)."""
+    rng = np.random.default_rng(20251020)
+    out = {}
+    k = 0
+    for (N, T, lag, sd) in ((64, 30, 3, 3.0), (100, 25, 5, 4.0), (33, 12, 1, 3.0), (17, 10, 20, 3.0), (8, 2, 3, 1.0), (8, 1, 3, 1.0)):
+        y = H.sim_lg(T, 300 + k, sd)
+        z, U = rng.standard_normal((T, lag, N)), rng.random(T)
+        o = H.o_blockpf(y, N, lag, z, U)            # only to learn which steps consume a uniform; the values stored are the reference's
+        r = H.r_blockpf(y, N, lag, z, U[o["resampled"] == 1])
+        out[f"N{k}"] = np.array(N); out[f"lag{k}"] = np.array(lag); out[f"y{k}"] = y; out[f"z{k}"] = z; out[f"U{k}"] = U
+        for key in ("weight", "values", "logNC"):
+            out[f"{key}{k}"] = np.asarray(r[key])
+        k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "blockpf_kat.npz"), **out)
+
+
+EXTRA = {"blockpf": blockpf_fixture}
+
+
 def main():
     assert H.ref_available(), "build oracle/_ref first (make -C oracle ref)"
+    if len(sys.argv) > 1:   # regenerate selected fixtures only
+        for name in sys.argv[1:]:
+            EXTRA[name]()
+        return
     rng = np.random.default_rng(20251019)
 
     # ---- 1. stableLogSumWeights / GetESS known answers (population.h:46-50, sampler.h:413-417)
@@ -107,6 +132,8 @@ def main():
     raw = np.loadtxt(os.path.join(ref_dir, "inst", "rawdata", "radiata-data.csv"), skiprows=1)
     assert raw.shape == (42, 3)
     np.savez(os.path.join(HERE, "radiata.npz"), data=raw)
+    for f in EXTRA.values():
+        f()
     print("golden fixtures written to", HERE)
 
 

@@ -302,3 +302,39 @@ def o_linreg(Data, N, z=None, U=None, Udraw=None, seed=0):
                               dp(None if Udraw is None else f64(Udraw)), ctypes.c_ulonglong(seed), dp(th), dp(w), dp(nc))
     assert rc == 0
     return {"theta": th.reshape(3, N).T, "weights": w, "logNC": float(nc[0])}
+
+
+def sim_lg(T, seed, obs_sd=1.0):
+    """Random walk + noise series for the block filter (R/blockpfGaussianOpt.R simGaussian: x_t = x_{t-1} + e, y = x + obs_sd e')."""
+    rng = np.random.default_rng(seed)
+    return np.cumsum(rng.standard_normal(T)) + obs_sd * rng.standard_normal(T)
+
+
+def blockpf_draw_count(t, lag):
+    return 1 if t < 2 else min(t, lag)
+
+
+def o_blockpf(y, N, lag, z=None, U=None, seed=0):
+    """Oracle port of blockpfGaussianOpt_impl.  z [T][lag][N] addressed normals, U [T] uniforms by step."""
+    y = f64(y); T = y.size
+    w, v, nc, ess = np.zeros(N), np.zeros(N * T), np.zeros(1), np.zeros(T)
+    rs, anc = np.zeros(T, dtype=np.int32), np.zeros((T, N), dtype=np.uint32)
+    zz = None if z is None else f64(z)
+    uu = None if U is None else f64(U)
+    oracle().smco_blockpf(dp(y), L(T), L(N), L(lag), dp(zz) if zz is not None else None, dp(uu) if uu is not None else None,
+                          ctypes.c_ulonglong(seed), dp(w), dp(v), dp(nc), dp(ess), rs.ctypes.data_as(IP), anc.ctypes.data_as(UP))
+    return {"weight": w, "values": v.reshape(T, N).T.copy(), "logNC": float(nc[0]), "ESS": ess, "resampled": rs, "ancestors": anc}
+
+
+def r_blockpf(y, N, lag, z, U_consumed):
+    """The compiled reference on the same draws: normals re-ordered into its consumption order (particle-major inside a step),
+    uniforms only for the steps that resample."""
+    y = f64(y); T = y.size
+    z = np.asarray(z).reshape(T, lag, N)
+    q = [z[t, :blockpf_draw_count(t, lag), :].T.reshape(-1) for t in range(T)]
+    r_clear(); r_push(normals=np.concatenate(q), uniforms=U_consumed)
+    w, v, nc = np.zeros(N), np.zeros(N * T), np.zeros(1)
+    rc = ref().smcref_blockpf(dp(y), L(T), L(N), L(lag), dp(w), dp(v), dp(nc))
+    assert rc == 0
+    assert ref().smcref_pending_normals() == 0 and ref().smcref_pending_uniforms() == 0
+    return {"weight": w, "values": v.reshape(T, N).T.copy(), "logNC": float(nc[0])}

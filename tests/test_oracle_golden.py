@@ -92,3 +92,14 @@ def test_pflineart_traces_bit_exact_vs_reference_fixtures():
         for key in ("Xm", "Xv", "Ym", "Yv", "logNC"):
             assert np.array_equal(r[key], g[f"{key}{k}"]), f"case {k} {key}"
         assert np.array_equal(r["ESS"][1:], g[f"ESS{k}"][1:])
+
+
+def test_blockpf_bit_exact_vs_reference_fixtures():
+    g = _load("blockpf_kat.npz")
+    resampled = 0
+    for k in range(int(g["ncases"])):
+        r = H.o_blockpf(g[f"y{k}"], int(g[f"N{k}"]), int(g[f"lag{k}"]), g[f"z{k}"], g[f"U{k}"])
+        assert r["logNC"] == float(g[f"logNC{k}"]), f"case {k}"
+        assert np.array_equal(r["weight"], g[f"weight{k}"]) and np.array_equal(r["values"], g[f"values{k}"]), f"case {k}"
+        resampled += int(r["resampled"].sum())
+    assert resampled >= 3   # the fixtures exercise the path copy on resampling

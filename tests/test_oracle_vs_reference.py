@@ -146,3 +146,14 @@ def test_pmmh_inner_filter_bit_exact():
         H.r_clear(); H.r_push(normals=z, uniforms=U)
         a = R.smcref_pmmh_filter(H.dp(H.f64(y)), H.L(T), H.L(N), H.D(9.3), H.D(1.2), mode, H.D(1.01 * N))
         assert a == H.o_pmmh_filter(y, N, 9.3, 1.2, mode, 1.01 * N, z=z, U=U)
+
+
+@pytest.mark.parametrize("N,T,lag,sd", [(50, 40, 4, 3.0), (128, 20, 2, 5.0), (9, 15, 30, 2.0), (31, 9, 1, 4.0)])
+def test_blockpf_bit_exact(N, T, lag, sd):
+    y = H.sim_lg(T, N + T, sd)
+    rng = np.random.default_rng(N * T + lag)
+    z, U = rng.standard_normal((T, lag, N)), rng.random(T)
+    o = H.o_blockpf(y, N, lag, z, U)
+    r = H.r_blockpf(y, N, lag, z, U[o["resampled"] == 1])
+    assert o["logNC"] == r["logNC"]
+    assert np.array_equal(o["weight"], r["weight"]) and np.array_equal(o["values"], r["values"])
