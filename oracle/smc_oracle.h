@@ -50,6 +50,13 @@ int smco_linreg(const double* data, long n_obs, long N, const double* z, const d
                 unsigned long long seed, double* theta_out, double* w_out, double* lognc_out);
 int smco_blockpf(const double* y, long T, long N, long lag_max, const double* z, const double* U, unsigned long long seed,
                  double* weight, double* values, double* lognc, double* ess_trace, int* resampled, unsigned* anc);
+int smco_csmc_lgss_run(const double* y, long T, long N, int mode, double phi, double var_evol, double x0, double var_obs,
+                       const double* ref, unsigned* refidx, const double* z, const double* U, int addressed,
+                       unsigned long long seed, double* lognc, unsigned* anc, double* values, double* logw, int* resampled,
+                       long* kt_out, long* nstoch);
+double smco_bpf_lgss(const double* y, long T, long N, int mode, double phi, double var_evol, double x0, double var_obs,
+                     const double* z, const double* U, unsigned long long seed, int* resampled);
+void smco_ancestor_lines(const unsigned* anc, const double* values, long T, long N, unsigned* lines, double* line_values);
 double smco_time_pfnonlinbs(const double* y, long T, long N, int mode, double threshold,
                             unsigned long long seed);
 

@@ -34,7 +34,32 @@ def blockpf_fixture():
     np.savez_compressed(os.path.join(HERE, "blockpf_kat.npz"), **out)
 
 
-EXTRA = {"blockpf": blockpf_fixture}
+def csmc_fixture():
+    """A chain of conditional bootstrap-filter runs on ONE reference conditionalSampler object (the driver's usage pattern,
+    src/cSMCexamples.cpp:81-125) on injected draws: logNC, AL history, reference-index state, ancestral lines."""
+    rng = np.random.default_rng(20251021)
+    par = (0.9, 1.0, 0.0, 1.0)
+    T, N = 20, 64
+    x, y = H.sim_lgss(T, 11)
+    H.r_csmc_open(y, N, par)
+    refidx = np.zeros(T, dtype=np.uint32)
+    out = {"y": y, "par": np.array(par), "N": np.array(N)}
+    k = 0
+    for sim in range(2):
+        reft = x + rng.standard_normal(T)
+        for mode in (H.MULTINOMIAL, H.RESIDUAL, H.STRATIFIED, H.SYSTEMATIC):
+            z, U = rng.standard_normal((T, N)), rng.random((T, N + 2))
+            o = H.o_csmc_run(y, N, mode, par, reft, refidx, z, U)   # only to learn the consumption pattern of the uniforms
+            r = H.r_csmc_run(mode, reft, T, N, z, H.csmc_uniform_queue(mode, U, o, N))
+            out[f"mode{k}"] = np.array(mode); out[f"ref{k}"] = reft; out[f"z{k}"] = z; out[f"U{k}"] = U
+            for key in ("logNC", "ancestors", "values", "logw", "resampled", "refidx", "lines", "line_values"):
+                out[f"{key}{k}"] = np.asarray(r[key])
+            k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "csmc_kat.npz"), **out)
+
+
+EXTRA = {"blockpf": blockpf_fixture, "csmc": csmc_fixture}
 
 
 def main():

@@ -338,3 +338,102 @@ def r_blockpf(y, N, lag, z, U_consumed):
     assert rc == 0
     assert ref().smcref_pending_normals() == 0 and ref().smcref_pending_uniforms() == 0
     return {"weight": w, "values": v.reshape(T, N).T.copy(), "logNC": float(nc[0])}
+
+
+# ---- conditional SMC on the linear-Gaussian model (compareNCestimates) -------------------------------------------------
+LP = ctypes.POINTER(ctypes.c_long)
+
+
+def sim_lgss(T, seed, phi=0.9, var_evol=1.0, var_obs=1.0, x0=0.0):
+    rng = np.random.default_rng(seed)
+    x = np.zeros(T)
+    prev = x0
+    for t in range(T):
+        x[t] = phi * prev + np.sqrt(var_evol) * rng.standard_normal()
+        prev = x[t]
+    return x, x + np.sqrt(var_obs) * rng.standard_normal(T)
+
+
+def o_csmc_run(y, N, mode, par, ref_traj, refidx, z=None, U=None, addressed=True, seed=0):
+    """One conditional run of the oracle port; `refidx` (uint32 [T]) is the persistent in/out reference-index state."""
+    y = f64(y); T = y.size
+    nc = np.zeros(1)
+    anc, val, lw = np.zeros((T, N), dtype=np.uint32), np.zeros((T, N)), np.zeros((T, N))
+    rs, kt, ns = np.zeros(T, dtype=np.int32), np.zeros(T, dtype=np.int64), np.zeros(T, dtype=np.int64)
+    zz = None if z is None else f64(z)
+    uu = None if U is None else f64(U)
+    rt = f64(ref_traj)
+    oracle().smco_csmc_lgss_run(dp(y), L(T), L(N), mode, D(par[0]), D(par[1]), D(par[2]), D(par[3]), dp(rt), refidx.ctypes.data_as(UP),
+                                dp(zz) if zz is not None else None, dp(uu) if uu is not None else None, 1 if addressed else 0,
+                                ctypes.c_ulonglong(seed), dp(nc), anc.ctypes.data_as(UP), dp(val), dp(lw), rs.ctypes.data_as(IP),
+                                kt.ctypes.data_as(LP), ns.ctypes.data_as(LP))
+    return {"logNC": float(nc[0]), "ancestors": anc, "values": val, "logw": lw, "resampled": rs, "Kt": kt, "nstoch": ns,
+            "refidx": refidx.copy()}
+
+
+def csmc_uniform_queue(mode, U, run, N):
+    """Addressed uniforms U [T][N+2] -> the sequence the reference consumes, given the port's trace of the same run."""
+    U = np.asarray(U).reshape(-1, N + 2)
+    q = []
+    for t in range(U.shape[0]):
+        if not run["resampled"][t]:
+            continue
+        kt = int(run["Kt"][t])
+        if mode == MULTINOMIAL:
+            q.extend(U[t, 2 + 1:2 + N])
+        elif mode == STRATIFIED:
+            q.append(U[t, 0]); q.extend(U[t, 2 + i] for i in range(N) if i != kt)
+        elif mode == SYSTEMATIC:
+            q.append(U[t, 0]); q.append(U[t, 1])
+        else:
+            q.append(U[t, 0]); q.extend(U[t, 2 + k] for k in range(int(run["nstoch"][t]), N) if k != kt)
+    return np.array(q, dtype=np.float64)
+
+
+def r_csmc_open(y, N, par):
+    y = f64(y)
+    ref().smcref_csmc_open(dp(y), L(y.size), L(N), D(par[0]), D(par[1]), D(par[2]), D(par[3]))
+
+
+def r_csmc_run(mode, ref_traj, T, N, z, uq):
+    r_clear(); r_push(normals=f64(z).reshape(-1), uniforms=uq if uq.size else None)
+    nc = np.zeros(1)
+    ri, rs = np.zeros(T, dtype=np.uint32), np.zeros(T, dtype=np.int32)
+    anc, lines = np.zeros((T, N), dtype=np.uint32), np.zeros((T, N), dtype=np.uint32)
+    val, lw, lv = np.zeros((T, N)), np.zeros((T, N)), np.zeros((T, N))
+    rt = f64(ref_traj)
+    rc = ref().smcref_csmc_run(mode, dp(rt), dp(nc), ri.ctypes.data_as(UP), anc.ctypes.data_as(UP), dp(val), dp(lw), rs.ctypes.data_as(IP),
+                               lines.ctypes.data_as(UP), dp(lv))
+    assert rc == 0
+    assert ref().smcref_pending_normals() == 0 and ref().smcref_pending_uniforms() == 0
+    return {"logNC": float(nc[0]), "ancestors": anc, "values": val, "logw": lw, "resampled": rs, "refidx": ri, "lines": lines,
+            "line_values": lv}
+
+
+def o_ancestor_lines(anc, values=None):
+    anc = np.ascontiguousarray(anc, dtype=np.uint32)
+    T, N = anc.shape
+    lines, lv = np.zeros((T, N), dtype=np.uint32), np.zeros((T, N))
+    v = None if values is None else f64(values)
+    oracle().smco_ancestor_lines(anc.ctypes.data_as(UP), dp(v) if v is not None else None, L(T), L(N), lines.ctypes.data_as(UP), dp(lv))
+    return lines, lv
+
+
+def o_bpf_lgss(y, N, mode, par, z=None, U=None, seed=0, want_flags=False):
+    y = f64(y)
+    o = oracle(); o.smco_bpf_lgss.restype = D
+    zz = None if z is None else f64(z)
+    uu = None if U is None else f64(U)
+    rs = np.zeros(y.size, dtype=np.int32)
+    v = o.smco_bpf_lgss(dp(y), L(y.size), L(N), mode, D(par[0]), D(par[1]), D(par[2]), D(par[3]), dp(zz) if zz is not None else None,
+                        dp(uu) if uu is not None else None, ctypes.c_ulonglong(seed), rs.ctypes.data_as(IP))
+    return (v, rs) if want_flags else v
+
+
+def r_bpf_lgss(mode, z, uq):
+    """Plain bootstrap filter of the compiled reference on the model opened by r_csmc_open."""
+    r_clear(); r_push(normals=f64(z).reshape(-1), uniforms=uq if uq.size else None)
+    nc = np.zeros(1)
+    assert ref().smcref_bpf_lgss_run(mode, dp(nc)) == 0
+    assert ref().smcref_pending_normals() == 0 and ref().smcref_pending_uniforms() == 0
+    return float(nc[0])

@@ -103,3 +103,16 @@ def test_blockpf_bit_exact_vs_reference_fixtures():
         assert np.array_equal(r["weight"], g[f"weight{k}"]) and np.array_equal(r["values"], g[f"values{k}"]), f"case {k}"
         resampled += int(r["resampled"].sum())
     assert resampled >= 3   # the fixtures exercise the path copy on resampling
+
+
+def test_conditional_sampler_chain_bit_exact_vs_reference_fixtures():
+    g = _load("csmc_kat.npz")
+    y, par, N = g["y"], tuple(g["par"]), int(g["N"])
+    refidx = np.zeros(y.size, dtype=np.uint32)
+    for k in range(int(g["ncases"])):
+        o = H.o_csmc_run(y, N, int(g[f"mode{k}"]), par, g[f"ref{k}"], refidx, g[f"z{k}"], g[f"U{k}"])
+        assert o["logNC"] == float(g[f"logNC{k}"]), k
+        for key in ("ancestors", "values", "logw", "resampled", "refidx"):
+            assert np.array_equal(o[key], g[f"{key}{k}"]), (k, key)
+        lines, lv = H.o_ancestor_lines(o["ancestors"], o["values"])
+        assert np.array_equal(lines, g[f"lines{k}"]) and np.array_equal(lv, g[f"line_values{k}"])

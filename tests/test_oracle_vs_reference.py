@@ -157,3 +157,44 @@ def test_blockpf_bit_exact(N, T, lag, sd):
     r = H.r_blockpf(y, N, lag, z, U[o["resampled"] == 1])
     assert o["logNC"] == r["logNC"]
     assert np.array_equal(o["weight"], r["weight"]) and np.array_equal(o["values"], r["values"])
+
+
+LGSS_PAR = (0.9, 1.0, 0.0, 1.0)   # phi, varStateEvol, stateInit, varObs
+
+
+def test_conditional_sampler_chain_bit_exact():
+    # a chain of runs on ONE conditionalSampler object, as the reference driver does (cSMCexamples.cpp:81-125): the
+    # reference-index state carries over between runs and modes
+    T, N = 16, 48
+    x, y = H.sim_lgss(T, 1)
+    rng = np.random.default_rng(5)
+    H.r_csmc_open(y, N, LGSS_PAR)
+    refidx = np.zeros(T, dtype=np.uint32)
+    seen = set()
+    for sim in range(3):
+        reft = x + rng.standard_normal(T)
+        for mode in (H.MULTINOMIAL, H.RESIDUAL, H.STRATIFIED, H.SYSTEMATIC):
+            z, U = rng.standard_normal((T, N)), rng.random((T, N + 2))
+            o = H.o_csmc_run(y, N, mode, LGSS_PAR, reft, refidx, z, U)
+            r = H.r_csmc_run(mode, reft, T, N, z, H.csmc_uniform_queue(mode, U, o, N))
+            assert o["logNC"] == r["logNC"]
+            for key in ("ancestors", "values", "logw", "refidx", "resampled"):
+                assert np.array_equal(o[key], r[key]), (sim, mode, key)
+            assert o["resampled"].sum() >= 2
+            lines, lv = H.o_ancestor_lines(o["ancestors"], o["values"])     # GetALineInd / GetALineSpace for every particle
+            assert np.array_equal(lines, r["lines"]) and np.array_equal(lv, r["line_values"])
+            seen.add(tuple(r["refidx"]))
+    assert len(seen) > 3   # the carried state really varies
+
+
+@pytest.mark.parametrize("mode", [H.STRATIFIED, H.SYSTEMATIC])
+def test_plain_lgss_filter_bit_exact(mode):
+    T, N = 30, 100
+    _, y = H.sim_lgss(T, 3)
+    rng = np.random.default_rng(mode)
+    per = 1 if mode == H.SYSTEMATIC else N + 1
+    z, U = rng.standard_normal((T, N)), rng.random((T, per))
+    H.r_csmc_open(y, N, LGSS_PAR)
+    v, flags = H.o_bpf_lgss(y, N, mode, LGSS_PAR, z, U, want_flags=True)
+    assert flags.sum() >= 3
+    assert v == H.r_bpf_lgss(mode, z, U[flags == 1].reshape(-1))
