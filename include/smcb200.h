@@ -190,6 +190,45 @@ int smcb200_blockpfGaussianOpt(const double* data_host, long n_data, long partic
                                const double* noise_host, const double* uniforms_host, double* weight_host, double* values_host,
                                double* lognc_host, double* ess_host, int* resampled_host, uint32_t* ancestors_host);
 
+/* ---- conditional SMC (reference inst/include/conditionalSampler.h, src/cSMCexamples.cpp, sampler.h:445-476) ------------ */
+
+/* Conditional bootstrap particle filters on the scalar linear-Gaussian model of the reference example
+ * (x_t = phi x_{t-1} + N(0, varStateEvol), x_0 = stateInit, y_t ~ N(x_t, varObs); cSMCexamples.cpp:141-218), HistoryType::AL,
+ * resampling at ESS < particles/2 with the conditional multinomial / residual / stratified / systematic schemes of
+ * conditionalSampler.h:377-655.
+ * Work is organised in CHAINS: a chain is what the reference does with one smc::conditionalSampler object -- runs executed in
+ * order, with the sampler's reference-index state carried from run to run (the reference driver uses a single object for every
+ * simulation and scheme, :76-125).  Chains are independent and run concurrently (one thread block each).
+ * Run r of chain c is entry c * runs_per_chain + r of modes_host (SMCB200_* resampling modes) and reference_host [runs][T].
+ * Outputs per run: lognc_host [runs] = GetLogNCPath(); optional refidx_host [runs][T] = GetReferenceValueIndex(t) after the run;
+ * optional AL history ancestors_host / values_host / logw_host [runs][T][particles] (History[t].GetAIndices(), post-resampling
+ * particle values, normalised log-weights) and resampled_host [runs][T].
+ * Optional injected draws: noise_host [runs][T][particles] standard normals; uniforms_host [runs][T][particles + 2]: entry 0 of a
+ * step draws K_t, entry 1 the systematic offset, entry 2 + i belongs to offspring slot i.  NULL -> Philox(seed). */
+int smcb200_conditionalBPF(const double* data_host, long T, long particles, double phi, double varStateEvol, double stateInit,
+                           double varObs, long n_chains, long runs_per_chain, const int* modes_host, const double* reference_host,
+                           uint64_t seed, const double* noise_host, const double* uniforms_host, double* lognc_host,
+                           uint32_t* refidx_host, uint32_t* ancestors_host, double* values_host, double* logw_host,
+                           int* resampled_host);
+
+/* Plain bootstrap filter on the same model (SamplerBPF of cSMCexamples.cpp:66-69,82-99): log normalising constant of one run.
+ * Injected draws as in smcb200_pfNonlinBS (noise [T][particles]; uniforms by step for the chosen mode). */
+int smcb200_lgssBPF(const double* data_host, long T, long particles, double phi, double varStateEvol, double stateInit, double varObs,
+                    int resample_mode, uint64_t seed, const double* noise_host, const double* uniforms_host, double* lognc_host);
+
+/* compareNCestimates_imp(data, lParticleNum, simNum, parInits{phi, varStateEvol, stateInit, varObs}, referenceTraj [T x simNum])
+ * (cSMCexamples.cpp:36-139): smcOut_host / csmcOut_host [simNum x 4] column-major, columns multinomial, residual, stratified,
+ * systematic.  independent_sims = 0 reproduces the reference's single conditional sampler object (one chain of 4 simNum runs,
+ * sequential by construction); independent_sims = 1 gives every simulation a fresh sampler (simNum concurrent chains of 4). */
+int smcb200_compareNCestimates(const double* data_host, long T, long particles, int simNum, double phi, double varStateEvol,
+                               double stateInit, double varObs, const double* referenceTraj_host, uint64_t seed, int independent_sims,
+                               double* smcOut_host, double* csmcOut_host);
+
+/* Ancestral lines of an AL history: lines_host [T][particles], column n = sampler::GetALineInd(n) (sampler.h:445-459);
+ * with values_host [T][particles] (scalar particle values per step) also line_values_host = GetALineSpace(n) (:461-476). */
+int smcb200_ancestor_lines(const uint32_t* ancestors_host, long T, long particles, const double* values_host, uint32_t* lines_host,
+                           double* line_values_host);
+
 #ifdef __cplusplus
 }
 #endif

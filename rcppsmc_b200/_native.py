@@ -63,6 +63,14 @@ def lib():
                                  _c_double_p, _c_double_p, _c_double_p, _c_double_p]
     L.smcb200_blockpfGaussianOpt.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, _c_double_p,
                                              _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_uint_p]
+    L.smcb200_conditionalBPF.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_long, ctypes.c_long, _c_int_p, _c_double_p, ctypes.c_uint64, _c_double_p, _c_double_p, _c_double_p,
+                                         _c_uint_p, _c_uint_p, _c_double_p, _c_double_p, _c_int_p]
+    L.smcb200_lgssBPF.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_int, ctypes.c_uint64, _c_double_p, _c_double_p, _c_double_p]
+    L.smcb200_compareNCestimates.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, _c_double_p, ctypes.c_uint64, ctypes.c_int, _c_double_p, _c_double_p]
+    L.smcb200_ancestor_lines.argtypes = [_c_uint_p, ctypes.c_long, ctypes.c_long, _c_double_p, _c_uint_p, _c_double_p]
     L.smcb200_pfNonlinBS_create.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_void_p)]
     L.smcb200_pfNonlinBS_create_island.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
@@ -303,6 +311,79 @@ def blockpfGaussianOpt(data, particles, lag, seed=1, noise=None, uniforms=None, 
     if diagnostics:
         out.update(ESS=ess, resampled=rs, ancestors=anc)
     return out
+
+
+def _lgss_par(parInits):
+    if isinstance(parInits, dict):
+        return tuple(float(parInits[k]) for k in ("phi", "varStateEvol", "stateInit", "varObs"))
+    return tuple(float(v) for v in parInits)
+
+
+def compareNCestimates(data, lParticleNum, simNum, parInits, referenceTraj, seed=1, independent_sims=False):
+    """Mirror of ``compareNCestimates_imp(data, lParticleNum, simNum, parInits, referenceTraj)`` (reference src/cSMCexamples.cpp:36-139):
+    dict with smcOut and csmcOut [simNum x 4] (columns multinomial, residual, stratified, systematic).  ``parInits`` is the
+    reference's list {phi, varStateEvol, stateInit, varObs}; ``referenceTraj`` is [T x simNum]."""
+    y = _f64(np.asarray(data).reshape(-1))
+    ref = np.asarray(referenceTraj, dtype=np.float64)
+    if ref.shape != (y.size, int(simNum)):
+        raise ValueError("referenceTraj must be [T x simNum]")
+    refc = np.ascontiguousarray(ref.T)   # column-major [T x simNum]
+    a, b = np.empty((4, int(simNum))), np.empty((4, int(simNum)))
+    phi, ve, x0, vo = _lgss_par(parInits)
+    _check(lib().smcb200_compareNCestimates(_dp(y), y.size, int(lParticleNum), int(simNum), phi, ve, x0, vo, _dp(refc), seed,
+                                            1 if independent_sims else 0, _dp(a), _dp(b)))
+    return {"smcOut": a.T, "csmcOut": b.T}
+
+
+def conditionalBPF(data, particles, parInits, modes, reference, runs_per_chain=None, seed=1, noise=None, uniforms=None, history=False):
+    """Chains of conditional bootstrap-filter runs (``smc::conditionalSampler`` on the LGSS example, HistoryType::AL).  ``modes`` [runs],
+    ``reference`` [runs][T]; runs are grouped into chains of ``runs_per_chain`` (default: one chain) that share the sampler's
+    reference-index state like runs on one reference sampler object.  Returns logNC [runs], refidx [runs][T] and, with
+    ``history``, the AL history (ancestors, values, logw [runs][T][N], resampled [runs][T])."""
+    y = _f64(np.asarray(data).reshape(-1))
+    T, N = y.size, int(particles)
+    modes = np.ascontiguousarray(modes, dtype=np.int32).reshape(-1)
+    runs = modes.size
+    rpc = runs if runs_per_chain is None else int(runs_per_chain)
+    if runs % rpc:
+        raise ValueError("runs must be a multiple of runs_per_chain")
+    ref = _f64(np.asarray(reference).reshape(runs, T))
+    zn, un = _f64(noise), _f64(uniforms)
+    nc, ridx = np.empty(runs), np.empty((runs, T), dtype=np.uint32)
+    anc = val = lw = rs = None
+    if history:
+        anc, val, lw = np.empty((runs, T, N), dtype=np.uint32), np.empty((runs, T, N)), np.empty((runs, T, N))
+        rs = np.empty((runs, T), dtype=np.int32)
+    phi, ve, x0, vo = _lgss_par(parInits)
+    _check(lib().smcb200_conditionalBPF(_dp(y), T, N, phi, ve, x0, vo, runs // rpc, rpc, modes.ctypes.data_as(_c_int_p), _dp(ref), seed,
+                                        _dp(zn), _dp(un), _dp(nc), ridx.ctypes.data_as(_c_uint_p),
+                                        anc.ctypes.data_as(_c_uint_p) if history else None, _dp(val), _dp(lw),
+                                        rs.ctypes.data_as(_c_int_p) if history else None))
+    out = {"logNC": nc, "refidx": ridx}
+    if history:
+        out.update(ancestors=anc, values=val, logw=lw, resampled=rs)
+    return out
+
+
+def lgssBPF(data, particles, parInits, resample_mode, seed=1, noise=None, uniforms=None):
+    """Log normalising constant of one plain bootstrap filter on the LGSS example (SamplerBPF of cSMCexamples.cpp:66-99)."""
+    y = _f64(np.asarray(data).reshape(-1))
+    nc = np.empty(1)
+    phi, ve, x0, vo = _lgss_par(parInits)
+    _check(lib().smcb200_lgssBPF(_dp(y), y.size, int(particles), phi, ve, x0, vo, int(resample_mode), seed, _dp(_f64(noise)), _dp(_f64(uniforms)), _dp(nc)))
+    return float(nc[0])
+
+
+def ancestor_lines(ancestors, values=None):
+    """``GetALineInd(n)`` for every particle n (columns of the returned [T][N] array) and, with ``values`` [T][N], ``GetALineSpace``
+    (reference sampler.h:445-476) from the per-step ancestor rows of an AL history."""
+    anc = np.ascontiguousarray(ancestors, dtype=np.uint32)
+    T, N = anc.shape
+    lines = np.empty((T, N), dtype=np.uint32)
+    v = _f64(values)
+    lv = np.empty((T, N)) if v is not None else None
+    _check(lib().smcb200_ancestor_lines(anc.ctypes.data_as(_c_uint_p), T, N, _dp(v), lines.ctypes.data_as(_c_uint_p), _dp(lv)))
+    return (lines, lv) if v is not None else lines
 
 
 class PfNonlinBS:

@@ -143,4 +143,36 @@ struct NonlinPMMH {
     __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
 };
 
+// Scalar linear-Gaussian state space model of the conditional-SMC example: reference src/cSMCexamples.cpp:141-200.
+// x_0 = stateInit (deterministic), x_t = phi x_{t-1} + N(0, varStateEvol), y_t ~ N(x_t, varObs); pfInitialise already moves
+// x_0 to x_1 and weights it with y[0] (:165-172).
+struct LGSS {
+    static constexpr int D = 1;
+    static constexpr int NZ_INIT = 1;
+    static constexpr int NZ_MOVE = 1;
+    static constexpr int NSHIFT = 0;
+    static constexpr int NOBS = 0;
+    struct Params {
+        const double* y;
+        double phi, sd_evol, x0, sd_obs, log_sd_obs;
+    };
+    __host__ __device__ static __forceinline__ double loglik(const Params& p, double yt, double x) {  // R nmath dnorm4, give_log (:152-156)
+        const double ln_sqrt_2pi = 0.918938533204672741780329736406;
+        double z = (yt - x) / p.sd_obs;
+        return -(ln_sqrt_2pi + 0.5 * z * z + p.log_sd_obs);
+    }
+    __device__ static __forceinline__ void init(double (&x)[D], double& lw, const Params& p, const double* z) {
+        x[0] = p.phi * p.x0 + (0.0 + p.sd_evol * z[0]);
+        lw = loglik(p, p.y[0], x[0]);
+    }
+    __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {
+        x[0] = p.phi * x[0] + (0.0 + p.sd_evol * z[0]);
+        lw += loglik(p, p.y[t], x[0]);
+    }
+    __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[1]) { h[0] = 0.0; }
+    __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[1]) { f[0] = 0.0; }
+    __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
+};
+
+
 }  // namespace smcb
