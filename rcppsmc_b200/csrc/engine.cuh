@@ -90,6 +90,18 @@ struct StepArgs {
 
 enum { PHASE_INIT = 0, PHASE_MOVE = 1, PHASE_OBSERVE = 2 };
 
+// Asynchronous global -> shared copies (LDGSTS): the data never passes through a register, so a copy in flight holds no
+// register scoreboard and cannot stall the instructions that recycle registers around it.
+// (destinations are 32-bit shared-window addresses, computed once per thread outside the particle loop)
+__device__ __forceinline__ void cp_async4(unsigned smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <class Model, int PHASE, bool INJECT, bool ISLAND = false>
 __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
     constexpr int D = Model::D, G = Model::NSHIFT, NOBS = Model::NOBS;
@@ -129,34 +141,58 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     const long long npairs = (n + 1) >> 1;
     const long long stride = (long long)gridDim.x * STEP_THREADS;
     const long long p0 = (long long)blockIdx.x * STEP_THREADS + tid;
+    // Single-GPU path: every link lands in shared memory through cp.async (each thread owns one slot per array and is the only
+    // reader of it, so no barrier is involved); measured with ncu, the register-destination version of this pipeline stalled
+    // on the scoreboards of freshly issued gathers whenever a register of an older, finished load was recycled.
+    constexpr bool ASYNC = !ISLAND && PHASE != PHASE_INIT;
+    __shared__ uint32_t s_mk[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];      // bitmap word, rank base
+    __shared__ uint32_t s_sp[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];      // surplus entries of the pair
+    __shared__ double s_x[ASYNC ? 2 : 1][D][ASYNC ? STEP_THREADS : 1];      // parents' state
+    __shared__ double s_lw[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];        // stored log-weights (no resampling last step)
+    const bool decode = PHASE != PHASE_INIT && resampled && !(a.dbg & 1);
+    // the thread's slots: array k of a family sits k * stride bytes after the first one
+    const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][tid]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][tid]);
+    const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][tid]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][tid]);
+    constexpr unsigned ST4 = STEP_THREADS * 4u, ST8 = STEP_THREADS * 8u;
     uint32_t mA = 0u, bA = 0u;                 // stage A result
     uint32_t ancB[2] = {0u, 0u};               // stage B result
+    uint32_t zfB = 0u, selfB = 0u;             // ASYNC stage B result: which slots take a surplus entry, own slot id
     double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result
     auto stageA = [&](long long p) {
-        if (PHASE != PHASE_INIT && resampled && p < npairs && !(a.dbg & 1)) {
+        if (decode && p < npairs) {
+            if (ASYNC) {
+                cp_async4(sa_mk, a.am.zmask + (p >> 4));
+                cp_async4(sa_mk + ST4, a.am.zbase + (p >> 4));
+            } else {
 #if SMCB_MASK_LOAD == 1
-            mA = __ldcg(a.am.zmask + (p >> 4));
-            bA = __ldcg(a.am.zbase + (p >> 4));
+                mA = __ldcg(a.am.zmask + (p >> 4));
+                bA = __ldcg(a.am.zbase + (p >> 4));
 #elif SMCB_MASK_LOAD == 2
-            mA = a.am.zmask[p >> 4];
-            bA = a.am.zbase[p >> 4];
+                mA = a.am.zmask[p >> 4];
+                bA = a.am.zbase[p >> 4];
 #else
-            mA = __ldg(a.am.zmask + (p >> 4));
-            bA = __ldg(a.am.zbase + (p >> 4));
+                mA = __ldg(a.am.zmask + (p >> 4));
+                bA = __ldg(a.am.zbase + (p >> 4));
 #endif
+            }
         }
     };
-    auto stageB = [&](long long p) {   // consumes mA/bA (loaded for this p one iteration ago)
+    auto stageB = [&](long long p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
         if (PHASE != PHASE_INIT && p < npairs) {
             const long long s0 = 2 * p;
             const uint32_t self0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc + s0) : (uint32_t)s0;   // global slot id
-            ancB[0] = self0; ancB[1] = self0 + 1u;
-            if (resampled && !(a.dbg & 1)) {
+            if (ASYNC) { selfB = self0; zfB = 0u; } else { ancB[0] = self0; ancB[1] = self0 + 1u; }
+            if (decode) {
+                if (ASYNC) { mA = s_mk[0][tid]; bA = s_mk[ASYNC ? 1 : 0][tid]; }
                 const uint32_t bit = (uint32_t)s0 & 31u;
                 const uint32_t below = mA & ((1u << bit) - 1u);
                 const uint32_t rank = bA + __popc(below);
                 const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
-                if (!ISLAND) {
+                if (ASYNC) {
+                    zfB = z0 | (z1 << 1);
+                    if (z0) cp_async4(sa_sp, a.am.surplus + rank);
+                    if (z1) cp_async4(sa_sp + ST4, a.am.surplus + rank + z0);
+                } else if (!ISLAND) {
                     if (z0) ancB[0] = __ldg(a.am.surplus + rank);
                     if (z1) ancB[1] = __ldg(a.am.surplus + rank + z0);
                 } else {
@@ -179,11 +215,23 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
         }
     };
-    auto stageC = [&](long long p) {   // consumes ancB
+    auto stageC = [&](long long p) {   // consumes the surplus entries fetched for this p one iteration ago
         if (PHASE != PHASE_INIT && p < npairs) {
             const long long s0 = 2 * p;
             const bool has1 = s0 + 1 < n;
-            if (!ISLAND) {
+            if (ASYNC) {
+                const uint32_t a0 = (zfB & 1u) ? s_sp[0][tid] : selfB;
+                const uint32_t a1 = (zfB & 2u) ? s_sp[ASYNC ? 1 : 0][tid] : selfB + 1u;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    cp_async8(sa_x + (unsigned)d * ST8, src[d] + a0);
+                    if (has1) cp_async8(sa_x + (unsigned)(D + d) * ST8, src[d] + a1);
+                }
+                if (!resampled) {
+                    cp_async8(sa_lw, a.lw + s0);
+                    if (has1) cp_async8(sa_lw + ST8, a.lw + s0 + 1);
+                }
+            } else if (!ISLAND) {
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     xC[0][d] = src[d][ancB[0]];
@@ -202,19 +250,32 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                     }
                 }
             }
-            if (!resampled) { lwC[0] = a.lw[s0]; lwC[1] = has1 ? a.lw[s0 + 1] : 0.0; }
+            if (!ASYNC && !resampled) { lwC[0] = a.lw[s0]; lwC[1] = has1 ? a.lw[s0 + 1] : 0.0; }
         }
     };
     // prologue: fill the pipeline
-    stageA(p0); stageB(p0); stageC(p0);
-    stageA(p0 + stride); stageB(p0 + stride);
-    stageA(p0 + 2 * stride);
+    if (ASYNC) {
+        stageA(p0); cp_async_commit(); cp_async_wait_all();
+        stageB(p0); stageA(p0 + stride); cp_async_commit(); cp_async_wait_all();
+        stageC(p0); stageB(p0 + stride); stageA(p0 + 2 * stride); cp_async_commit();
+    } else {
+        stageA(p0); stageB(p0); stageC(p0);
+        stageA(p0 + stride); stageB(p0 + stride);
+        stageA(p0 + 2 * stride);
+    }
 
     for (long long p = p0; p < npairs; p += stride) {
         const long long s0 = 2 * p;
         const bool has1 = s0 + 1 < n;
         double x[2][D], lwv[2];
         if (PHASE != PHASE_INIT) {
+#pragma unroll
+            if (ASYNC) {   // everything issued one iteration ago has had a whole iteration to land
+                cp_async_wait_all();
+#pragma unroll
+                for (int d = 0; d < D; ++d) { xC[0][d] = s_x[0][d][tid]; xC[1][d] = has1 ? s_x[ASYNC ? 1 : 0][d][tid] : 0.0; }
+                if (!resampled) { lwC[0] = s_lw[0][tid]; lwC[1] = has1 ? s_lw[ASYNC ? 1 : 0][tid] : 0.0; }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -225,6 +286,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             stageC(p + stride);
             stageB(p + 2 * stride);
             stageA(p + 3 * stride);
+            if (ASYNC) cp_async_commit();
             if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {

@@ -22,7 +22,7 @@ namespace smcb {
 #define SMCB_SCAN_THREADS 128
 #endif
 #ifndef SMCB_SCAN_MINB
-#define SMCB_SCAN_MINB 7
+#define SMCB_SCAN_MINB 6
 #endif
 constexpr int SCAN_THREADS = SMCB_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 8;
@@ -331,6 +331,7 @@ inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TIL
 // Stage state lives in shared memory (double-buffered), not registers.
 constexpr int SCAN_PAD = SCAN_TILE + SCAN_TILE / SCAN_ITEMS;   // blocked layout with one pad word per thread
 struct ScanSmem {
+    double stage[SCAN_TILE];               // S0 -> S1: raw input of the next tile, landed by cp.async while the other stages run
     double cum[2][SCAN_PAD];               // S1 -> S2: tile-relative inclusive weight mass per slot (exact: multiples of 2^-52)
     int c[2][SCAN_PAD];                    // S2 -> S3: children handed out up to each slot; pad word = value before the thread's run
     int zrel[2][SCAN_THREADS];             // S2 -> S3: zero-count slots before the thread's run, tile-relative
@@ -362,27 +363,55 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
     // children handed out before this rank's first slot (0 on a single GPU)
     const int cstart = ISLAND ? children_upto<MODE, POW2>(mass0, a, nthr, nd, inv_n, dRand, step) : 0;
 
-    // tiles held by the stages: t1 enters S1 this iteration, t2 is in S2, t3 in S3 (-1 = empty)
-    int t2 = -1, t3 = -1;
+    // S0: asynchronous copy of a tile's input into shared memory; every thread stages exactly the slots it will read in S1,
+    // so S1 needs no barrier, only its own cp.async group to have landed.
+    const unsigned sa_stage = (unsigned)__cvta_generic_to_shared(&S.stage[tid]);
+    auto prefetch = [&](int t) {
+        if (t >= 0) {
+            const long long base = (long long)t * SCAN_TILE;
+            const bool full = base + SCAN_TILE <= n;
+#pragma unroll
+            for (int r = 0; r < SCAN_ITEMS; ++r) {
+                const int i = r * SCAN_THREADS + tid;
+                if (full || base + i < n) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa_stage + (unsigned)(r * SCAN_THREADS * 8)), "l"(a.in + base + i) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // tiles held by the stages: t0 is being staged, t1 enters S1 this iteration, t2 is in S2, t3 in S3 (-1 = empty)
+    int t2 = -1, t3 = -1, tn;
+    if (tid == 0) S.tile[0] = (int)atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    tn = S.tile[0] < ntiles ? S.tile[0] : -1;
+    prefetch(tn);
+    __syncthreads();
     for (int it = 0;; ++it) {
         const int b1 = it & 1, b2 = b1 ^ 1;   // cum buffer written by S1 / read by S2; c buffer written by S2 = b2, read by S3 = b1
         if (tid == 0) S.tile[0] = (int)atomicAdd(a.ticket, 1u);
         __syncthreads();
-        int t1 = S.tile[0];
-        if (t1 >= ntiles) t1 = -1;
-        if (t1 < 0 && t2 < 0 && t3 < 0) break;
+        int t0 = S.tile[0];
+        if (t0 >= ntiles) t0 = -1;
+        const int t1 = tn;
+        if (t0 < 0 && t1 < 0 && t2 < 0 && t3 < 0) break;
 
-        // ================= S1: load, quantise, block scan, publish aggregate =================
+        // ================= S1: staged input -> registers, restage the next tile, quantise, block scan, publish =================
         if (t1 >= 0) {
             const long long base = (long long)t1 * SCAN_TILE;
             const bool full = base + SCAN_TILE <= n;
             double* sq = S.cum[b1];
+            double raw[SCAN_ITEMS];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < SCAN_ITEMS; ++r) raw[r] = S.stage[r * SCAN_THREADS + tid];
+            prefetch(t0);
 #pragma unroll
             for (int r = 0; r < SCAN_ITEMS; ++r) {
                 const int i = r * SCAN_THREADS + tid;
                 double q = 0.0;
                 if (full || base + i < n) {
-                    const double w = (SRC == SRC_LOGW) ? fm_exp(a.in[base + i] - lse) : a.in[base + i];
+                    const double w = (SRC == SRC_LOGW) ? fm_exp(raw[r] - lse) : raw[r];
                     q = (w + 1.0) - 1.0;                  // round to the 2^-52 grid (ulp of [1,2))
                 }
                 sq[i + (i >> 3)] = q;
@@ -546,6 +575,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
         if (tid == 0) S.tile[2] = S.tile[1];   // zero-slot aggregate of the tile moving from S2 to S3
         t3 = t2;
         t2 = t1;
+        tn = t0;
     }
 }
 
