@@ -323,7 +323,7 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
         h->mode = resample_mode;
         h->kev_used = 0;
         if (h->profile) {
-            while (h->kev.size() < (size_t)(2 * h->T + 2)) { cudaEvent_t e; SMCB_CUDA(cudaEventCreate(&e)); h->kev.push_back(e); }
+            while (h->kev.size() < (size_t)(3 * h->T + 2)) { cudaEvent_t e; SMCB_CUDA(cudaEventCreate(&e)); h->kev.push_back(e); }
             smcb200_pf* hp = h;
             s.SetAfterLaunchHook([hp]() { if (hp->kev_used < hp->kev.size()) cudaEventRecord(hp->kev[hp->kev_used++], hp->stream); });
             SMCB_CUDA(cudaEventRecord(h->kev[h->kev_used++], h->stream));
@@ -403,17 +403,25 @@ int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launc
     return guarded([&]() -> int {
         if (!h || !move_ms || !move_launches || !scan_ms || !scan_launches) throw std::invalid_argument("null argument");
         if (!h->ran || !h->profile || h->kev_used < 3) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: run with profiling enabled first");
-        if (h->s->island()) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: not available in island mode");
         if (h->mode != SMCB200_SYSTEMATIC && h->mode != SMCB200_STRATIFIED) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: per-kernel split is defined for SYSTEMATIC / STRATIFIED runs");
         SMCB_CUDA(cudaEventSynchronize(h->kev[h->kev_used - 1]));
-        // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1
-        double mv = 0, sc = 0; long nm = 0, ns = 0;
+        // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1.
+        // Island mode has a weight-mass pass in front of every scan (init, mass, scan, (move, mass, scan) x (T-1), observe);
+        // it is reported as part of the scan time, and separately on stderr when SMCB200_PROF_PRINT is set.
+        double mv = 0, sc = 0, mass = 0; long nm = 0, ns = 0;
         const size_t nint = h->kev_used - 1;
+        const bool isl = h->s->island();
         for (size_t i = 0; i < nint; ++i) {
             float ms; SMCB_CUDA(cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]));
             if (i == 0 || i == nint - 1) continue;           // init and the final moment pass are not counted
-            if (i % 2 == 1) { sc += ms; ++ns; } else { mv += ms; ++nm; }
+            if (!isl) { if (i % 2 == 1) { sc += ms; ++ns; } else { mv += ms; ++nm; } }
+            else if (i % 3 == 1) { sc += ms; mass += ms; }
+            else if (i % 3 == 2) { sc += ms; ++ns; }
+            else { mv += ms; ++nm; }
         }
+        if (isl && getenv("SMCB200_PROF_PRINT"))
+            fprintf(stderr, "[smcb200] island rank %d: k_step %.1f us, k_mass_total %.1f us, k_resample_scan %.1f us per step\n", h->s->rank(),
+                    1e3 * mv / (nm ? nm : 1), 1e3 * mass / (ns ? ns : 1), 1e3 * (sc - mass) / (ns ? ns : 1));
         *move_ms = (float)mv; *move_launches = nm; *scan_ms = (float)sc; *scan_launches = ns;
         return SMCB200_OK;
     });

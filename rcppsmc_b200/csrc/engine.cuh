@@ -141,74 +141,65 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     const long long npairs = (n + 1) >> 1;
     const long long stride = (long long)gridDim.x * STEP_THREADS;
     const long long p0 = (long long)blockIdx.x * STEP_THREADS + tid;
-    // Single-GPU path: every link lands in shared memory through cp.async (each thread owns one slot per array and is the only
-    // reader of it, so no barrier is involved); measured with ncu, the register-destination version of this pipeline stalled
-    // on the scoreboards of freshly issued gathers whenever a register of an older, finished load was recycled.
-    constexpr bool ASYNC = !ISLAND && PHASE != PHASE_INIT;
-    __shared__ uint32_t s_mk[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];      // bitmap word, rank base
-    __shared__ uint32_t s_sp[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];      // surplus entries of the pair
-    __shared__ double s_x[ASYNC ? 2 : 1][D][ASYNC ? STEP_THREADS : 1];      // parents' state
-    __shared__ double s_lw[ASYNC ? 2 : 1][ASYNC ? STEP_THREADS : 1];        // stored log-weights (no resampling last step)
+    // Every link lands in shared memory through cp.async (each thread owns one slot per array and is the only reader of it, so
+    // no barrier is involved).  Measured with ncu, a register-destination version of this pipeline stalled on the scoreboards
+    // of freshly issued gathers whenever a register of an older, finished load was recycled.  In island mode the source of a
+    // copy may be a peer's slab (surplus entry or parent state on another island): same instruction, NVLink underneath.
+    constexpr bool ASYNC = PHASE != PHASE_INIT;
+    __shared__ uint32_t s_mk[2][ASYNC ? STEP_THREADS : 1];      // bitmap word, rank base
+    __shared__ uint32_t s_sp[2][ASYNC ? STEP_THREADS : 1];      // surplus entries of the pair
+    __shared__ double s_x[2][D][ASYNC ? STEP_THREADS : 1];      // parents' state
+    __shared__ double s_lw[2][ASYNC ? STEP_THREADS : 1];        // stored log-weights (no resampling last step)
     const bool decode = PHASE != PHASE_INIT && resampled && !(a.dbg & 1);
     // the thread's slots: array k of a family sits k * stride bytes after the first one
-    const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][tid]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][tid]);
-    const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][tid]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][tid]);
+    const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][ASYNC ? tid : 0]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][ASYNC ? tid : 0]);
+    const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][ASYNC ? tid : 0]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][ASYNC ? tid : 0]);
     constexpr unsigned ST4 = STEP_THREADS * 4u, ST8 = STEP_THREADS * 8u;
-    uint32_t mA = 0u, bA = 0u;                 // stage A result
-    uint32_t ancB[2] = {0u, 0u};               // stage B result
-    uint32_t zfB = 0u, selfB = 0u;             // ASYNC stage B result: which slots take a surplus entry, own slot id
-    double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result
+    // island mode: this rank's window of the global zero-slot ranking / surplus list / slot numbering (uniform over the kernel)
+    const long long zoff_mine = (ISLAND && decode) ? a.ctrl->zoff[a.isl.rank] : 0, eoff_mine = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank] : 0;
+    const long long eoff_next = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank + 1] : 0, eoff_all = (ISLAND && decode) ? a.ctrl->eoff[a.isl.world] : 0;
+    const uint32_t slot_lo = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;
+    uint32_t zfB = 0u, selfB = 0u;             // stage B result: bit h = slot h takes its surplus entry, bit 2+h = slot h takes particle 0
+    double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result, read back from shared memory
     auto stageA = [&](long long p) {
-        if (decode && p < npairs) {
-            if (ASYNC) {
-                cp_async4(sa_mk, a.am.zmask + (p >> 4));
-                cp_async4(sa_mk + ST4, a.am.zbase + (p >> 4));
-            } else {
-#if SMCB_MASK_LOAD == 1
-                mA = __ldcg(a.am.zmask + (p >> 4));
-                bA = __ldcg(a.am.zbase + (p >> 4));
-#elif SMCB_MASK_LOAD == 2
-                mA = a.am.zmask[p >> 4];
-                bA = a.am.zbase[p >> 4];
-#else
-                mA = __ldg(a.am.zmask + (p >> 4));
-                bA = __ldg(a.am.zbase + (p >> 4));
-#endif
-            }
+        if (ASYNC && decode && p < npairs) {
+            cp_async4(sa_mk, a.am.zmask + (p >> 4));
+            cp_async4(sa_mk + ST4, a.am.zbase + (p >> 4));
         }
     };
     auto stageB = [&](long long p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
-        if (PHASE != PHASE_INIT && p < npairs) {
+        if (ASYNC && p < npairs) {
             const long long s0 = 2 * p;
-            const uint32_t self0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc + s0) : (uint32_t)s0;   // global slot id
-            if (ASYNC) { selfB = self0; zfB = 0u; } else { ancB[0] = self0; ancB[1] = self0 + 1u; }
+            selfB = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc + s0) : (uint32_t)s0;   // global slot id
+            zfB = 0u;
             if (decode) {
-                if (ASYNC) { mA = s_mk[0][tid]; bA = s_mk[ASYNC ? 1 : 0][tid]; }
+                const uint32_t mA = s_mk[0][tid], bA = s_mk[1][tid];
                 const uint32_t bit = (uint32_t)s0 & 31u;
                 const uint32_t below = mA & ((1u << bit) - 1u);
                 const uint32_t rank = bA + __popc(below);
                 const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
-                if (ASYNC) {
+                if (!ISLAND) {
                     zfB = z0 | (z1 << 1);
                     if (z0) cp_async4(sa_sp, a.am.surplus + rank);
                     if (z1) cp_async4(sa_sp + ST4, a.am.surplus + rank + z0);
-                } else if (!ISLAND) {
-                    if (z0) ancB[0] = __ldg(a.am.surplus + rank);
-                    if (z1) ancB[1] = __ldg(a.am.surplus + rank + z0);
                 } else {
                     // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         if (h == 0 ? z0 : z1) {
-                            const long long m = a.ctrl->zoff[a.isl.rank] + rank + (h ? z0 : 0u);
-                            uint32_t par = 0u;   // beyond the available surplus children: particle 0 (sampler.h:845)
-                            if (m < a.ctrl->eoff[a.isl.world]) {
+                            const long long m = zoff_mine + rank + (h ? z0 : 0u);
+                            if (m >= eoff_mine && m < eoff_next) {   // the usual case: the entry is in this island's own list
+                                cp_async4(sa_sp + (unsigned)h * ST4, a.am.surplus + (m - eoff_mine));
+                                zfB |= 1u << h;
+                            } else if (m < eoff_all) {
                                 int o = 0;
                                 while (o + 1 < a.isl.world && m >= a.ctrl->eoff[o + 1]) ++o;
                                 const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.isl.base[o] + a.isl.off_surplus);
-                                par = sp[m - a.ctrl->eoff[o]];
+                                cp_async4(sa_sp + (unsigned)h * ST4, sp + (m - a.ctrl->eoff[o]));
+                                zfB |= 1u << h;
+                            } else {
+                                zfB |= 4u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
                             }
-                            ancB[h] = par;
                         }
                     }
                 }
@@ -216,41 +207,39 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         }
     };
     auto stageC = [&](long long p) {   // consumes the surplus entries fetched for this p one iteration ago
-        if (PHASE != PHASE_INIT && p < npairs) {
+        if (ASYNC && p < npairs) {
             const long long s0 = 2 * p;
             const bool has1 = s0 + 1 < n;
-            if (ASYNC) {
-                const uint32_t a0 = (zfB & 1u) ? s_sp[0][tid] : selfB;
-                const uint32_t a1 = (zfB & 2u) ? s_sp[ASYNC ? 1 : 0][tid] : selfB + 1u;
+            uint32_t anc[2];
+            anc[0] = (zfB & 1u) ? s_sp[0][tid] : ((zfB & 4u) ? 0u : selfB);
+            anc[1] = (zfB & 2u) ? s_sp[1][tid] : ((zfB & 8u) ? 0u : selfB + 1u);
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    cp_async8(sa_x + (unsigned)d * ST8, src[d] + a0);
-                    if (has1) cp_async8(sa_x + (unsigned)(D + d) * ST8, src[d] + a1);
-                }
-                if (!resampled) {
-                    cp_async8(sa_lw, a.lw + s0);
-                    if (has1) cp_async8(sa_lw + ST8, a.lw + s0 + 1);
-                }
-            } else if (!ISLAND) {
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !has1) break;
+                if (!ISLAND) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    xC[0][d] = src[d][ancB[0]];
-                    xC[1][d] = has1 ? src[d][ancB[1]] : 0.0;
-                }
-            } else {
-                // the parent may live on another island: read it from the owner's slab over NVLink
+                    for (int d = 0; d < D; ++d) cp_async8(sa_x + (unsigned)(h * D + d) * ST8, src[d] + anc[h]);
+                } else {
+                    // the parent may live on another island: copy it from the owner's slab over NVLink
+                    const uint32_t rel = anc[h] - slot_lo;
+                    if (rel < (uint32_t)a.isl.n_loc) {   // the usual case under systematic / stratified resampling: a local parent
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int o = (int)(ancB[h] / (uint32_t)a.isl.n_loc);
-                    const long long li = (long long)ancB[h] - (long long)o * a.isl.n_loc;
+                        for (int d = 0; d < D; ++d) cp_async8(sa_x + (unsigned)(h * D + d) * ST8, src[d] + rel);
+                    } else {
+                        const int o = (int)(anc[h] / (uint32_t)a.isl.n_loc);
+                        const long long li = (long long)anc[h] - (long long)o * a.isl.n_loc;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const double* xs = reinterpret_cast<const double*>(a.isl.base[o] + (parity ? a.isl.off_xb[d] : a.isl.off_xa[d]));
-                        xC[h][d] = (h == 0 || has1) ? xs[li] : 0.0;
+                        for (int d = 0; d < D; ++d) {
+                            const double* xs = reinterpret_cast<const double*>(a.isl.base[o] + (parity ? a.isl.off_xb[d] : a.isl.off_xa[d]));
+                            cp_async8(sa_x + (unsigned)(h * D + d) * ST8, xs + li);
+                        }
                     }
                 }
             }
-            if (!ASYNC && !resampled) { lwC[0] = a.lw[s0]; lwC[1] = has1 ? a.lw[s0 + 1] : 0.0; }
+            if (!resampled) {
+                cp_async8(sa_lw, a.lw + s0);
+                if (has1) cp_async8(sa_lw + ST8, a.lw + s0 + 1);
+            }
         }
     };
     // prologue: fill the pipeline
@@ -258,10 +247,6 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         stageA(p0); cp_async_commit(); cp_async_wait_all();
         stageB(p0); stageA(p0 + stride); cp_async_commit(); cp_async_wait_all();
         stageC(p0); stageB(p0 + stride); stageA(p0 + 2 * stride); cp_async_commit();
-    } else {
-        stageA(p0); stageB(p0); stageC(p0);
-        stageA(p0 + stride); stageB(p0 + stride);
-        stageA(p0 + 2 * stride);
     }
 
     for (long long p = p0; p < npairs; p += stride) {
@@ -269,12 +254,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         const bool has1 = s0 + 1 < n;
         double x[2][D], lwv[2];
         if (PHASE != PHASE_INIT) {
-#pragma unroll
             if (ASYNC) {   // everything issued one iteration ago has had a whole iteration to land
                 cp_async_wait_all();
 #pragma unroll
-                for (int d = 0; d < D; ++d) { xC[0][d] = s_x[0][d][tid]; xC[1][d] = has1 ? s_x[ASYNC ? 1 : 0][d][tid] : 0.0; }
-                if (!resampled) { lwC[0] = s_lw[0][tid]; lwC[1] = has1 ? s_lw[ASYNC ? 1 : 0][tid] : 0.0; }
+                for (int d = 0; d < D; ++d) { xC[0][d] = s_x[0][d][tid]; xC[1][d] = has1 ? s_x[1][d][tid] : 0.0; }
+                if (!resampled) { lwC[0] = s_lw[0][tid]; lwC[1] = has1 ? s_lw[1][tid] : 0.0; }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -560,6 +544,7 @@ public:
 
     // ---- island plumbing: one IPC handle per rank, exchanged by the host (torch.distributed in bench.py / tests)
     bool island() const { return world_ > 1; }
+    int rank() const { return rank_; }
     void ExportIpc(cudaIpcMemHandle_t* out) { SMCB_CUDA(cudaIpcGetMemHandle(out, slab_)); }
     void ImportPeers(const cudaIpcMemHandle_t* handles) {
         for (int h = 0; h < world_; ++h) {
@@ -696,7 +681,7 @@ private:
             MassArgs m{};
             m.lw = lw_; m.n = n_; m.lse_ptr = &ctrl_->lse; m.enable_ptr = &ctrl_->resampled; m.step_ptr = &ctrl_->T;
             m.partial = mass_partial_ + 8; m.done = (unsigned int*)mass_partial_; m.mass_offset_out = &ctrl_->mass_offset; m.isl = isl_;
-            int g = grid_move_ < 1000 ? grid_move_ : 1000;
+            int g = 2 * grid_move_ < 1000 ? 2 * grid_move_ : 1000;
             k_mass_total<<<g, 256, 0, stream_>>>(m);
             SMCB_CUDA(cudaGetLastError());
             if (after_launch_) after_launch_();

@@ -630,9 +630,20 @@ struct MassArgs {
 static __global__ void __launch_bounds__(256) k_mass_total(MassArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     const double lse = *a.lse_ptr;
-    unsigned long long sum = 0ull;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256)
-        sum += (unsigned long long)__double2ll_rn(fm_exp(a.lw[i] - lse) * TWO52);
+    // Same grid arithmetic as the scan: q = (w + 1) - 1 is w rounded to a multiple of 2^-52, and sums of such values below 2
+    // are exact in fp64 in any order.  Four independent slots per thread and iteration (two 16-byte loads).
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const long long nq = a.n >> 2;
+    const double2* lw2 = reinterpret_cast<const double2*>(a.lw);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nq; i += (long long)gridDim.x * 256) {
+        const double2 u = lw2[2 * i], v = lw2[2 * i + 1];
+        s0 += (fm_exp(u.x - lse) + 1.0) - 1.0; s1 += (fm_exp(u.y - lse) + 1.0) - 1.0;
+        s2 += (fm_exp(v.x - lse) + 1.0) - 1.0; s3 += (fm_exp(v.y - lse) + 1.0) - 1.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(a.n & 3)) s0 += (fm_exp(a.lw[(nq << 2) + threadIdx.x] - lse) + 1.0) - 1.0;
+    // every lane total is a multiple of 2^-52 below 2 (the weights sum to 1): the conversions are exact
+    unsigned long long sum = (unsigned long long)__double2ll_rn(s0 * TWO52) + (unsigned long long)__double2ll_rn(s1 * TWO52) +
+                             (unsigned long long)__double2ll_rn(s2 * TWO52) + (unsigned long long)__double2ll_rn(s3 * TWO52);
     __shared__ unsigned long long s_w[8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
