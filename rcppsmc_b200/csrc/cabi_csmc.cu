@@ -426,9 +426,9 @@ extern "C" int smcb200_ancestor_lines(const uint32_t* ancestors_host, long T, lo
     return guarded([&]() -> int {
         if (!ancestors_host || T < 1 || particles < 1 || !lines_host) throw std::invalid_argument("ancestor_lines: ancestors [T][N] and lines output required");
         if ((values_host == nullptr) != (line_values_host == nullptr)) throw std::invalid_argument("ancestor_lines: values and line_values go together");
-        require_device();
         const size_t tn = (size_t)T * (size_t)particles;
         for (size_t k = 0; k < tn; ++k) if (ancestors_host[k] >= (uint32_t)particles) throw std::invalid_argument("ancestor_lines: ancestor index out of range");
+        require_device();
         DevBuf anc(sizeof(uint32_t) * tn), lines(sizeof(uint32_t) * tn), val, lv;
         SMCB_CUDA(cudaMemcpy(anc.p, ancestors_host, sizeof(uint32_t) * tn, cudaMemcpyHostToDevice));
         if (values_host) {

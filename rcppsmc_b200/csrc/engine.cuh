@@ -490,6 +490,9 @@ public:
         if (world < 1 || world > ISL_MAX || rank < 0 || rank >= world) throw std::invalid_argument("island rank/world out of range");
         n_glob_ = n * world;
         if (world > 1 && (n_glob_ > 2147483647LL || (n & 1))) throw std::invalid_argument("island mode needs an even local particle count and world*n < 2^31");
+        // experiment switches for profiling sessions (0 in production), read once per sampler
+        { const char* e = getenv("SMCB200_DBG_STEP"); dbg_step_ = e ? atoi(e) : 0; }
+        { const char* e = getenv("SMCB200_DBG_SCAN"); dbg_scan_ = e ? atoi(e) : 0; }
         ntiles_ = scan_tiles(n);
         surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
         // ---- slab layout (256-byte aligned sub-allocations)
@@ -663,7 +666,7 @@ private:
         a.lw = lw_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
         a.status = status_; a.nstatus = 3 * ntiles_; a.params = params_; a.seed = seed_;
         a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_; a.isl = isl_;
-        { const char* e = getenv("SMCB200_DBGS"); a.dbg = e ? atoi(e) : 0; }
+        a.dbg = dbg_step_;
         return a;
     }
     void enqueue_resample() {
@@ -672,7 +675,7 @@ private:
         s.ustrat = ustrat_; s.step_ptr = &ctrl_->T; s.seed = seed_; s.ticket = &ctrl_->ticket;
         s.ws.statusA = status_; s.ws.statusB = status_ + ntiles_; s.ws.statusC = status_ + 2 * ntiles_;
         s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
-        { const char* e = getenv("SMCB200_DBG"); s.dbg = e ? atoi(e) : 0; }
+        s.dbg = dbg_scan_;
         s.n_glob = n_glob_; s.surplus_cap = surplus_cap_; s.isl = isl_;
         if (island()) {
             if (mode_ != SYSTEMATIC && mode_ != STRATIFIED)
@@ -710,6 +713,7 @@ private:
 
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
+    int dbg_step_ = 0, dbg_scan_ = 0;
     unsigned char* slab_ = nullptr;
     size_t slab_bytes_ = 0;
     IslandInfo isl_{};

@@ -12,5 +12,5 @@ f.set_data(y); f.set_profile(True)
 for it in range(3):
     f.run(smc.SYSTEMATIC); f.sync()
 mv, nm, sc, ns = f.kernel_ms()
-print(f"DBGS={os.environ.get('SMCB200_DBGS','0')} DBG={os.environ.get('SMCB200_DBG','0')} N=2^{logn} total={f.elapsed_ms():.3f} ms  k_step={1e3*mv/nm:.1f} us/launch  k_scan={1e3*sc/ns:.1f} us/launch", flush=True)
+print(f"STEP={os.environ.get('SMCB200_DBG_STEP','0')} SCAN={os.environ.get('SMCB200_DBG_SCAN','0')} N=2^{logn} total={f.elapsed_ms():.3f} ms  k_step={1e3*mv/nm:.1f} us/launch  k_scan={1e3*sc/ns:.1f} us/launch", flush=True)
 f.close()

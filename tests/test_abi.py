@@ -50,6 +50,32 @@ def test_compute_fails_loudly_without_device():
         smc.resample(smc.SYSTEMATIC, np.ones(4) / 4, [0.5])
     with pytest.raises(smc.SmcError, match="no CUDA device"):
         smc.pfNonlinBS(np.zeros(5), 100, resample_mode=smc.SYSTEMATIC)
+    with pytest.raises(smc.SmcError, match="no CUDA device"):
+        smc.blockpfGaussianOpt(np.zeros(5), 100, 2)
+    with pytest.raises(smc.SmcError, match="no CUDA device"):
+        smc.compareNCestimates(np.zeros(5), 100, 2, (0.9, 1.0, 0.0, 1.0), np.zeros((5, 2)))
+    with pytest.raises(smc.SmcError, match="no CUDA device"):
+        smc.conditionalBPF(np.zeros(5), 100, (0.9, 1.0, 0.0, 1.0), [smc.SYSTEMATIC], np.zeros((1, 5)))
+    with pytest.raises(smc.SmcError, match="no CUDA device"):
+        smc.ancestor_lines(np.zeros((3, 4), dtype=np.uint32))
+
+
+def test_argument_errors_are_reported_through_the_status_channel():
+    # invalid arguments are rejected before any device work (status SMCB200_ERR_INVALID + smcb200_last_error text),
+    # the C-ABI counterpart of smc::exception / Rcpp::stop in the reference drivers
+    import rcppsmc_b200 as smc
+    with pytest.raises(smc.SmcError, match="lag >= 1"):
+        smc.blockpfGaussianOpt(np.zeros(5), 100, 0)
+    with pytest.raises(smc.SmcError, match="particles >= 1"):
+        smc.blockpfGaussianOpt(np.zeros(5), 0, 2)
+    with pytest.raises(smc.SmcError, match="unknown resampling mode"):
+        smc.conditionalBPF(np.zeros(5), 100, (0.9, 1.0, 0.0, 1.0), [7], np.zeros((1, 5)))
+    with pytest.raises(smc.SmcError, match="T >= 2"):
+        smc.conditionalBPF(np.zeros(1), 100, (0.9, 1.0, 0.0, 1.0), [smc.SYSTEMATIC], np.zeros((1, 1)))
+    with pytest.raises(smc.SmcError, match="out of range"):
+        smc.ancestor_lines(np.full((2, 3), 9, dtype=np.uint32))
+    with pytest.raises(ValueError):
+        smc.compareNCestimates(np.zeros(5), 100, 2, (0.9, 1.0, 0.0, 1.0), np.zeros((4, 2)))
 
 
 def test_product_does_not_touch_the_oracle():
