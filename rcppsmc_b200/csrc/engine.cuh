@@ -29,7 +29,7 @@ constexpr int MAX_SHIFT = 4;
 #define SMCB_MASK_LOAD 0
 #endif
 #ifndef SMCB_STEP_MINB
-#define SMCB_STEP_MINB 3
+#define SMCB_STEP_MINB 2
 #endif
 #ifndef SMCB_STEP_THREADS
 #define SMCB_STEP_THREADS 256
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     for (long long i = (long long)blockIdx.x * STEP_THREADS + tid; i < a.nstatus; i += (long long)gridDim.x * STEP_THREADS)
         a.status[i] = 0ull;
 
-    LseAcc<G> acc;
-    acc.clear();
+    LseAcc<G> acc, acc1;   // one per particle of the pair, merged after the loop
+    acc.clear(); acc1.clear();
     double obs0 = 0.0, obs[NOBS > 0 ? NOBS : 1];
 #pragma unroll
     for (int j = 0; j < NOBS; ++j) obs[j] = 0.0;
@@ -273,11 +273,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             if (ASYNC) cp_async_commit();
             if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && !has1) break;
+                for (int h = 0; h < 2; ++h) {   // no early exit: the two particles' arithmetic interleaves (a missing odd tail weighs 0)
                     double f[NOBS > 0 ? NOBS : 1];
                     Model::observe(x[h], shift, f);
                     double w = resampled ? 1.0 : fm_exp(lwv[h]);
+                    if (h == 1) w = has1 ? w : 0.0;
                     obs0 += w;
 #pragma unroll
                     for (int j = 0; j < NOBS; ++j) obs[j] = fma(w, f[j], obs[j]);
@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
             double lwo[2] = {0.0, 0.0};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !has1) break;
+            for (int h = 0; h < 2; ++h) {   // straight-line for both particles: independent dependency chains, one accumulator each
                 double lw;
                 if (PHASE == PHASE_INIT) {
                     Model::init(x[h], lw, a.params, z[h]);   // moveset.h:133-138
@@ -317,7 +316,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 lwo[h] = lw;
                 double hs[G > 0 ? G : 1];
                 Model::shift_stat(x[h], hs);
-                if (a.dbg & 8) { acc.s += lw; acc.m = 0.0; acc.q = 1.0; } else acc.add(lw, hs);
+                if (h == 1) lw = has1 ? lw : -INFINITY;   // a missing odd tail contributes nothing
+                if (h == 0) acc.add(lw, hs); else acc1.add(lw, hs);
             }
             if (!(a.dbg & 2)) {
                 if (has1) {   // both particles of the pair: one 16-byte store per array (s0 is even, arrays are 256-byte aligned)
@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     constexpr int NF = 4 + G + NOBS;  // m, s, q, obs0, g[G], obs[NOBS]
     __shared__ double s_red[STEP_THREADS / 32][NF];
     __shared__ bool s_last;
+    acc.merge(acc1);
     acc.warp_reduce();
     obs0 = warp_sum(obs0);
 #pragma unroll
