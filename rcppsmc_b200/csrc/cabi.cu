@@ -205,7 +205,8 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
                 SMCB_CUDA(cudaMemcpy(us.p, uniforms_host, sizeof(double) * n, cudaMemcpyHostToDevice));
                 DevBuf cum(sizeof(unsigned long long) * n), extra(sizeof(unsigned long long) * 2);
                 SMCB_CUDA(cudaMemset(extra.p, 0, sizeof(unsigned long long) * 2));
-                DrawWs dw{cum.as<unsigned long long>(), counts.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1)};
+                DevBuf bucket(sizeof(uint32_t) * draw_bucket_entries(n));
+                DrawWs dw{cum.as<unsigned long long>(), counts.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1), bucket.as<uint32_t>()};
                 launch_resample_draws<SRC_WEIGHTS>(mode, w.as<double>(), n, nullptr, nullptr, us.as<double>(), nullptr, 0, ticket, ws, dw, am, tail, 0);
                 SMCB_CUDA(cudaDeviceSynchronize());
             }

@@ -237,7 +237,8 @@ void run_linreg(const double* data_host, long n_obs, long particles, uint64_t se
     }
     SMCB_CUDA(cudaMemcpy(ctrl.p, &h, sizeof h, cudaMemcpyHostToDevice));
     ScanWs ws{status.as<unsigned long long>(), status.as<unsigned long long>() + ntiles, status.as<unsigned long long>() + 2 * ntiles};
-    DrawWs dw{cum.as<unsigned long long>(), count.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1)};
+    DevBuf bucket(sizeof(uint32_t) * draw_bucket_entries(n));
+    DrawWs dw{cum.as<unsigned long long>(), count.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1), bucket.as<uint32_t>()};
     for (long g = 0; g < n_obs; ++g) {
         if (g == 0) k_la_init<<<grid, 256, 0, st>>>(a);
         else k_la_reweight<<<grid, 256, 0, st>>>(a);

@@ -700,8 +700,8 @@ private:
             case STRATIFIED: launch_resample_scan<SRC_LOGW, STRATIFIED>(s, stream_); break;
             case MULTINOMIAL:
             case RESIDUAL: {
-                if (!cum_) { cum_ = dalloc<unsigned long long>(n_); count_ = dalloc<int>(n_); }
-                DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2};
+                if (!cum_) { cum_ = dalloc<unsigned long long>(n_); count_ = dalloc<int>(n_); bucket_ = dalloc<uint32_t>(draw_bucket_entries(n_)); }
+                DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2, bucket_};
                 launch_resample_draws<SRC_LOGW>(mode_, lw_, n_, &ctrl_->lse, &ctrl_->resampled, udraw_, &ctrl_->T, seed_,
                                                 &ctrl_->ticket, s.ws, dw, am_, nullptr, stream_);
                 break;
@@ -739,6 +739,7 @@ private:
     const double* udraw_ = nullptr;   // MULTINOMIAL / RESIDUAL injected uniforms U[step][n]
     unsigned long long* cum_ = nullptr;
     int* count_ = nullptr;
+    uint32_t* bucket_ = nullptr;
     int grid_init_ = 1, grid_move_ = 1, grid_scan_ = 1;
     long long steps_ = 0;
     std::function<void()> after_launch_;

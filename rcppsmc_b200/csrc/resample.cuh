@@ -885,7 +885,41 @@ struct DrawArgs {
     const long long* step_ptr;
     unsigned long long seed;
     int* count;                      // [n] in/out: += children per parent
+    uint32_t* bucket;                // [2 * nb + 2] search guide, nb = draw_buckets(n)
+    int log_nb;
 };
+
+// Guide table of the inverse-CDF search.  A draw t falls in bucket t >> s (s chosen so that the total mass spans between nb
+// and 2 nb buckets); bucket[b] = first slot whose cumulative mass reaches b << s.  The answer for t (first k with cum[k] > t)
+// then lies in [bucket[b], bucket[b + 1]], on average 8-16 slots = one or two cache lines, instead of the ~12 scattered
+// lines a full binary search over 2^24 slots misses on.  Neighbouring buckets search neighbouring regions, so building the
+// table is cheap.
+inline int draw_log_buckets(long long n) {
+    int lb = 0;
+    while ((16LL << lb) < n) ++lb;   // ~ n / 16 buckets
+    return lb;
+}
+__device__ __forceinline__ int draw_bucket_shift(unsigned long long Q, int log_nb) {
+    const int bits = 64 - __clzll((long long)(Q | 1ull));   // Q < 2^bits
+    return bits > log_nb + 1 ? bits - (log_nb + 1) : 0;     // nb <= Q >> s < 2 nb
+}
+
+static __global__ void __launch_bounds__(256) k_draw_buckets(DrawArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const long long n = a.n;
+    const unsigned long long Q = a.cum[n - 1];
+    const int s = draw_bucket_shift(Q, a.log_nb);
+    const long long nb = (long long)(Q >> s) + 2;   // buckets 0 .. (Q >> s) + 1
+    for (long long b = (long long)blockIdx.x * 256 + threadIdx.x; b < nb; b += (long long)gridDim.x * 256) {
+        const unsigned long long thr = (unsigned long long)b << s;
+        long long l = 0, h = n - 1;                   // min k with cum[k] >= thr (n - 1 if none)
+        while (l < h) {
+            long long mid = (l + h) >> 1;
+            if (a.cum[mid] >= thr) h = mid; else l = mid + 1;
+        }
+        a.bucket[b] = (uint32_t)l;
+    }
+}
 
 static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
@@ -893,6 +927,7 @@ static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
     const long long ndraws = a.floor_total ? n - (long long)*a.floor_total : n;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
     const unsigned long long Q = a.cum[n - 1];
+    const int s = draw_bucket_shift(Q, a.log_nb);
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ndraws; j += (long long)gridDim.x * blockDim.x) {
         unsigned long long m;
         if (a.uniforms) m = (unsigned long long)(a.uniforms[step * n + j] * 9007199254740992.0);
@@ -900,7 +935,8 @@ static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
         // t = floor(m Q / 2^53)
         unsigned long long hi = __umul64hi(m, Q), lo = m * Q;
         unsigned long long t = (hi << 11) | (lo >> 53);
-        long long l = 0, h = n - 1;  // min k with cum[k] > t
+        const unsigned long long b = t >> s;
+        long long l = a.bucket[b], h = a.bucket[b + 1];  // min k with cum[k] > t lies in [l, h]
         while (l < h) {
             long long mid = (l + h) >> 1;
             if (__ldg(a.cum + mid) > t) h = mid; else l = mid + 1;
@@ -909,10 +945,12 @@ static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
     }
 }
 
+// Right shift of the 52-bit residual fractions: their sum over n slots must stay below 2^61, inside the 62-bit payload of a
+// look-back status word (a total of ~2^62 at n = 2^20 used to spill into the flag bits of the last tiles' prefixes).
 inline int residual_shift(long long n) {
     int nb = 0;
     while ((1LL << nb) < n) ++nb;
-    return nb > 11 ? nb - 11 : 0;
+    return nb > 9 ? nb - 9 : 0;
 }
 
 struct DrawWs {                      // extra workspace of the MULTINOMIAL / RESIDUAL path
@@ -920,7 +958,9 @@ struct DrawWs {                      // extra workspace of the MULTINOMIAL / RES
     int* count;                      // [n]
     unsigned long long* floor_total; // device scalar (zero on entry)
     unsigned int* ticket2;           // second tile ticket (zero on entry)
+    uint32_t* bucket;                // [draw_bucket_entries(n)] search guide of the inverse-CDF draws
 };
+inline size_t draw_bucket_entries(long long n) { return ((size_t)2 << draw_log_buckets(n)) + 2; }
 
 // weights -> integer scan -> iid draws -> children counts -> ancestor map.  `ticket`, `ticket2`, `floor_total` and the
 // three status arrays must be zero on entry.
@@ -951,7 +991,11 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
     DrawArgs d{};
     d.cum = dw.cum; d.n = n; d.enable_ptr = enable_ptr; d.floor_total = mode == RESIDUAL ? dw.floor_total : nullptr;
     d.uniforms = uniforms; d.step_ptr = step_ptr; d.seed = seed; d.count = dw.count;
-    long long need = (n + 255) / 256;
+    d.bucket = dw.bucket; d.log_nb = draw_log_buckets(n);
+    long long need = ((2LL << d.log_nb) + 2 + 255) / 256;
+    k_draw_buckets<<<(int)(need < grid_draw ? need : grid_draw), 256, 0, stream>>>(d);
+    SMCB_CUDA(cudaGetLastError());
+    need = (n + 255) / 256;
     k_multinomial_draw<<<(int)(need < grid_draw ? need : grid_draw), 256, 0, stream>>>(d);
     SMCB_CUDA(cudaGetLastError());
     CountMapArgs m{dw.count, n, enable_ptr, dw.ticket2, ws, am, tail_info};

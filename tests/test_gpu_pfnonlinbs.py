@@ -120,3 +120,24 @@ def test_full_size_properties(smc):
     small = smc.pfNonlinBS(y, 1 << 16, resample_mode=H.SYSTEMATIC, seed=8)
     assert np.all(np.abs(small["mean"] - out["mean"]) < 0.5)
     f.close()
+
+
+@pytest.mark.parametrize("mode", [H.RESIDUAL, H.MULTINOMIAL])
+def test_repeated_runs_on_one_handle_are_bit_identical(smc, mode):
+    # same seed, same handle, 2^20 particles: every run must reproduce the first one bit for bit
+    T, N = 40, 1 << 20
+    _, y = H.sim_nonlin(60, 1)
+    f = smc.PfNonlinBS(N, T, seed=1)
+    f.set_data(y[:T])
+    first = None
+    for _ in range(4):
+        f.run(mode)
+        f.sync()
+        out = f.read()
+        idx = f.read_ancestors()
+        if first is None:
+            first = (out["logNC"].copy(), idx.copy())
+            assert np.bincount(idx.astype(np.int64), minlength=N).sum() == N
+        else:
+            assert np.array_equal(out["logNC"], first[0]) and np.array_equal(idx, first[1])
+    f.close()

@@ -105,6 +105,23 @@ def test_native_multinomial_residual_bit_exact_vs_oracle(smc, n, mode):
         assert np.array_equal(idx, oidx)
 
 
+@pytest.mark.parametrize("n", [1 << 20, (1 << 21) + 7])
+def test_residual_large_fraction_mass_stays_inside_the_status_payload(smc, n):
+    # almost every slot has n w = 0.9: the residual fractions sum to ~0.9 n 2^(52 - shift), which must stay below the 62-bit
+    # payload of the look-back status words (it once reached 2^62 at n = 2^20 and corrupted the flags of the last tiles)
+    rng = np.random.default_rng(n)
+    w = np.full(n, 0.9 / n)
+    heavy = rng.choice(n, size=64, replace=False)
+    w[heavy] += (1.0 - w.sum()) / 64
+    w = H.o_quantise(w / w.sum())
+    U = rng.random(n)
+    idx, cnt = smc.resample(H.RESIDUAL, w, U, return_counts=True)
+    oidx, ocnt = H.o_resample_w(H.RESIDUAL, w, U)
+    assert cnt.sum() == n and np.array_equal(cnt, ocnt) and np.array_equal(idx, oidx)
+    again = smc.resample(H.RESIDUAL, w, U)
+    assert np.array_equal(idx, again)
+
+
 def test_resample_degenerate_weights(smc):
     # one particle carries (almost) everything: exercises the heavy-parent paths of the surplus writer
     for n in (5000, 1 << 18):
