@@ -340,6 +340,7 @@ struct PlainLgss {
     PlainLgss(const double* y_host, long T_, long particles, uint64_t seed) : s(particles, T_, seed, 0), y(sizeof(double) * T_), T(T_), n(particles) {
         SMCB_CUDA(cudaMemcpy(y.p, y_host, sizeof(double) * T, cudaMemcpyHostToDevice));
     }
+    bool allow_graph = false;   // set by callers that run many filters of one shape
     double run(int mode, double phi, double var_evol, double x0, double var_obs, uint64_t seed, const double* noise_host, const double* unif_host) {
         s.SetResampleParams(mode, 0.5);                               // cSMCexamples.cpp:82
         s.SetParams(lgss_params(y.as<double>(), phi, var_evol, x0, var_obs));
@@ -357,8 +358,7 @@ struct PlainLgss {
         }
         s.SetInjectedNoise(zn, mode == SMCB200_SYSTEMATIC ? un : nullptr, mode == SMCB200_STRATIFIED ? un : nullptr,
                            (mode == SMCB200_MULTINOMIAL || mode == SMCB200_RESIDUAL) ? un : nullptr);
-        s.Initialise();
-        for (long t = 1; t < T; ++t) s.Iterate();
+        s.RunFilter(T, /*use_graph=*/allow_graph && !noise_host && !unif_host);
         return s.ReadCtrl().lognc_path;
     }
 };
@@ -400,8 +400,9 @@ extern "C" int smcb200_compareNCestimates(const double* data_host, long T, long 
         const int order[4] = {SMCB200_MULTINOMIAL, SMCB200_RESIDUAL, SMCB200_STRATIFIED, SMCB200_SYSTEMATIC};   // cSMCexamples.cpp:82-125
         // plain bootstrap filters: column c of smcOut is order[c]
         PlainLgss f(data_host, T, particles, seed);
-        for (int i = 0; i < simNum; ++i)
-            for (int c = 0; c < 4; ++c)
+        f.allow_graph = simNum >= 16;
+        for (int c = 0; c < 4; ++c)          // scheme-major: one captured graph per scheme serves all simulations
+            for (int i = 0; i < simNum; ++i)
                 smcOut_host[(size_t)c * simNum + i] =
                     f.run(order[c], phi, varStateEvol, stateInit, varObs, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(4 * i + c + 1), nullptr, nullptr);
         // conditional filters: run (i, c) uses referenceTraj.col(i); one chain reproduces the reference's single sampler object

@@ -45,14 +45,16 @@ extern "C" int smcb200_nonLinPMMH(const double* data_host, long T, long particle
         auto filter_loglik = [&](long it, double sigv, double sigw) -> double {   // Initialise(); IterateUntil(T-1); GetLogNCPath()
             NonlinPMMH::Params p{y.as<double>(), cterm.as<double>(), sigv, sigw, std::log(sigw)};
             s.SetParams(p);
+            const double dyn[3] = {sigv, sigw, std::log(sigw)};   // the same three values, as seen by a replayed graph
+            s.SetDynamicParams(dyn, 3);
             s.SetSeed(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(it + 1));
             const double* zn = nullptr; const double* un = nullptr;
             if (filter_noise_host) { SMCB_CUDA(cudaMemcpy(noise.p, filter_noise_host + (size_t)it * per_noise, sizeof(double) * per_noise, cudaMemcpyHostToDevice)); zn = noise.as<double>(); }
             if (filter_unif_host) { SMCB_CUDA(cudaMemcpy(unif.p, filter_unif_host + (size_t)it * per_unif, sizeof(double) * per_unif, cudaMemcpyHostToDevice)); un = unif.as<double>(); }
             s.SetInjectedNoise(zn, resample_mode == SMCB200_SYSTEMATIC ? un : nullptr, resample_mode == SMCB200_STRATIFIED ? un : nullptr,
                                (resample_mode == SMCB200_MULTINOMIAL || resample_mode == SMCB200_RESIDUAL) ? un : nullptr);
-            s.Initialise();
-            for (long t = 1; t < T; ++t) s.Iterate();
+            // graph replay pays off after ~60 filters (capture + instantiation of a 4 T-node graph); injected draws are re-uploaded per filter: eager
+            s.RunFilter(T, /*use_graph=*/!filter_noise_host && !filter_unif_host && M >= 64);
             return s.ReadCtrl().lognc_path;
         };
         // outer-chain randomness: Rcpp::rnorm(M, 0, 0.15), Rcpp::rnorm(M, 0, 0.08), Rcpp::runif(M) (nonLinPMMH.cpp:72-74)

@@ -58,6 +58,9 @@ struct Ctrl {
     unsigned long long mass_offset;  // integer weight mass of all lower ranks (start of this rank's cumulative scan)
     long long zoff[ISL_MAX + 1];     // zero-count slots before each rank (exclusive prefix; [world] = total)
     long long eoff[ISL_MAX + 1];     // surplus-list entries before each rank
+    // what may change between two filters of the same shape (so that a captured CUDA graph of the filter can be replayed):
+    unsigned long long seed;         // Philox key of this run
+    double mparam[4];                // model parameters picked up by Model::load_dynamic (e.g. the PMMH proposal)
 };
 
 struct Traces {             // device arrays of length Tcap
@@ -115,6 +118,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     const double lse_prev = a.ctrl->lse;
     const double log_n = a.ctrl->log_n;
     const int parity = a.ctrl->parity;
+    const unsigned long long seed = a.ctrl->seed;
+    typename Model::Params prm = a.params;
+    Model::load_dynamic(prm, a.ctrl->mparam);
     double shift[G > 0 ? G : 1];
 #pragma unroll
     for (int j = 0; j < G; ++j) shift[j] = a.ctrl->shift[j];
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
 #pragma unroll
                 for (int k = 0; k < NZ; ++k) {
                     if (a.dbg & 4) { z[0][k] = 0.3 + 1e-9 * (double)p; z[1][k] = -0.2; }
-                    else philox_normal2(a.seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur,
+                    else philox_normal2(seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur,
                                         (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) + p : p), k, z[0][k], z[1][k]);
                 }
             }
@@ -307,11 +313,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             for (int h = 0; h < 2; ++h) {   // straight-line for both particles: independent dependency chains, one accumulator each
                 double lw;
                 if (PHASE == PHASE_INIT) {
-                    Model::init(x[h], lw, a.params, z[h]);   // moveset.h:133-138
+                    Model::init(x[h], lw, prm, z[h]);   // moveset.h:133-138
                     lw = lw - log_n;                          // sampler.h:495
                 } else {
                     lw = lwv[h];
-                    Model::move(tcur, x[h], lw, a.params, z[h]);  // moveset.h:162-168
+                    Model::move(tcur, x[h], lw, prm, z[h]);  // moveset.h:162-168
                 }
                 lwo[h] = lw;
                 double hs[G > 0 ? G : 1];
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 for (int j = 0; j < G; ++j) c->shift[j] = b.g[j] / b.s;
                 double U;
                 if (a.ures) U = a.ures[tcur];
-                else U = u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
+                else U = u64_to_unit(philox_draw(seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
                 c->u_res = U;
                 if (tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
             }
@@ -542,6 +548,9 @@ public:
     ~Sampler() {
         for (int h = 0; h < world_; ++h) if (h != rank_ && isl_.base[h]) cudaIpcCloseMemHandle(isl_.base[h]);
         for (void* p : allocs_) cudaFree(p);
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (graph_stream_) cudaStreamDestroy(graph_stream_);
+        if (ctrl_stage_) cudaFreeHost(ctrl_stage_);
     }
     Sampler(const Sampler&) = delete;
     Sampler& operator=(const Sampler&) = delete;
@@ -567,6 +576,8 @@ public:
     }
     void SetParams(const typename Model::Params& p) { params_ = p; }
     void SetSeed(unsigned long long seed) { seed_ = seed; }
+    // Up to four model parameters that travel through the control block (Model::load_dynamic) instead of the kernel arguments.
+    void SetDynamicParams(const double* m, int count) { for (int k = 0; k < 4; ++k) dyn_[k] = k < count ? m[k] : 0.0; }
     // Injected randomness (parity testing): device pointers, reference consumption order.
     void SetInjectedNoise(const double* znoise, const double* ures, const double* ustrat, const double* udraw = nullptr) {
         znoise_ = znoise; ures_ = ures; ustrat_ = ustrat; udraw_ = udraw;
@@ -574,11 +585,14 @@ public:
 
     // sampler.h:481-550 (up to and including the resampling decision; the resampling pass itself is enqueued here too)
     void Initialise() {
-        Ctrl h{};
         if (!peers_ready_) throw std::runtime_error("island sampler: ImportPeers() has not been called");
         ++isl_.epoch;
-        h.thr = thr_; h.log_n = std::log((double)n_glob_); h.parity = 1;  // init writes buffer A (dst of parity 1)
-        SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        if (capturing_) {   // graph node: re-uploads whatever the staging copy holds at replay time
+            SMCB_CUDA(cudaMemcpyAsync(ctrl_, ctrl_stage_, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
+        } else {
+            Ctrl h = fresh_ctrl();
+            SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        }
         StepArgs<Model> a = args();
         if (island()) { no_inject(); k_step<Model, PHASE_INIT, false, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a); }
         else if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
@@ -600,6 +614,55 @@ public:
         ++steps_;
     }
     void IterateUntil(long long t_end) { while (steps_ - 1 < t_end) Iterate(); }
+
+    // Initialise() + (T - 1) x Iterate() for filters that are run again and again with the same shape (PMMH inner filters, the
+    // simulation loop of compareNCestimates): at 10^4..10^5 particles a step's kernels finish faster than the host can launch
+    // them, so the whole filter is captured ONCE into a CUDA graph and replayed with one launch.  Every decision of a step is
+    // already taken on the device; what differs between replays (seed, dynamic model parameters, threshold) is re-uploaded by
+    // the graph's first node from a pinned staging copy of the control block.  The first call runs eagerly (allocations,
+    // occupancy queries), the graph is rebuilt when the resampling mode, length or injected-draw pointers change.
+    // Returns with the filter finished when it was replayed from a graph; an eager run is only enqueued.
+    void RunFilter(long long T, bool use_graph = true) {
+        const GraphKey key{mode_, T, znoise_, ures_, ustrat_, udraw_};
+        const bool have = graph_exec_ && key == graph_key_;
+        if (!use_graph || island() || after_launch_ || (!have && !(graph_warm_ && key == warm_key_))) {
+            Initialise();   // first filter of this shape: eager (lazy allocations and occupancy queries happen here)
+            for (long long t = 1; t < T; ++t) Iterate();
+            graph_warm_ = true; warm_key_ = key;
+            return;
+        }
+        if (!ctrl_stage_) SMCB_CUDA(cudaMallocHost((void**)&ctrl_stage_, sizeof(Ctrl)));
+        if (!graph_stream_) SMCB_CUDA(cudaStreamCreate(&graph_stream_));   // blocking stream: ordered with the legacy stream
+        if (!graph_exec_ || !(key == graph_key_)) {
+            if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+            SMCB_CUDA(cudaStreamSynchronize(stream_));
+            cudaStream_t saved = stream_;
+            stream_ = graph_stream_;
+            capturing_ = true;
+            cudaGraph_t g = nullptr;
+            SMCB_CUDA(cudaStreamBeginCapture(graph_stream_, cudaStreamCaptureModeThreadLocal));
+            try {
+                Initialise();
+                for (long long t = 1; t < T; ++t) Iterate();
+            } catch (...) {
+                cudaStreamEndCapture(graph_stream_, &g);
+                if (g) cudaGraphDestroy(g);
+                stream_ = saved; capturing_ = false;
+                throw;
+            }
+            cudaError_t e = cudaStreamEndCapture(graph_stream_, &g);
+            stream_ = saved; capturing_ = false;
+            SMCB_CUDA(e);
+            e = cudaGraphInstantiate(&graph_exec_, g, 0);
+            cudaGraphDestroy(g);
+            SMCB_CUDA(e);
+            graph_key_ = key;
+        }
+        *ctrl_stage_ = fresh_ctrl();
+        steps_ = T;
+        SMCB_CUDA(cudaGraphLaunch(graph_exec_, graph_stream_));
+        SMCB_CUDA(cudaStreamSynchronize(graph_stream_));
+    }
     // Fused Integrate for the current (last) population: closes the observable trace.
     void ObserveFinal() {
         StepArgs<Model> a = args();
@@ -647,6 +710,17 @@ public:
     int grid_scan() const { return grid_scan_; }
 
 private:
+    struct GraphKey {
+        int mode; long long T; const double* z; const double* u0; const double* u1; const double* u2;
+        bool operator==(const GraphKey& o) const { return mode == o.mode && T == o.T && z == o.z && u0 == o.u0 && u1 == o.u1 && u2 == o.u2; }
+    };
+    Ctrl fresh_ctrl() const {
+        Ctrl h{};
+        h.thr = thr_; h.log_n = std::log((double)n_glob_); h.parity = 1;  // init writes buffer A (dst of parity 1)
+        h.seed = seed_;
+        for (int k = 0; k < 4; ++k) h.mparam[k] = dyn_[k];
+        return h;
+    }
     void no_inject() const {
         if (znoise_ || ures_ || ustrat_ || udraw_) throw std::invalid_argument("island mode does not take injected draws");
     }
@@ -673,7 +747,7 @@ private:
     void enqueue_resample() {
         ScanArgs s{};
         s.in = lw_; s.n = n_; s.lse_ptr = &ctrl_->lse; s.enable_ptr = &ctrl_->resampled; s.u_ptr = &ctrl_->u_res;
-        s.ustrat = ustrat_; s.step_ptr = &ctrl_->T; s.seed = seed_; s.ticket = &ctrl_->ticket;
+        s.ustrat = ustrat_; s.step_ptr = &ctrl_->T; s.seed = seed_; s.seed_ptr = &ctrl_->seed; s.ticket = &ctrl_->ticket;
         s.ws.statusA = status_; s.ws.statusB = status_ + ntiles_; s.ws.statusC = status_ + 2 * ntiles_;
         s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
         s.dbg = dbg_scan_;
@@ -703,7 +777,7 @@ private:
                 if (!cum_) { cum_ = dalloc<unsigned long long>(n_); count_ = dalloc<int>(n_); bucket_ = dalloc<uint32_t>(draw_bucket_entries(n_)); }
                 DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2, bucket_};
                 launch_resample_draws<SRC_LOGW>(mode_, lw_, n_, &ctrl_->lse, &ctrl_->resampled, udraw_, &ctrl_->T, seed_,
-                                                &ctrl_->ticket, s.ws, dw, am_, nullptr, stream_);
+                                                &ctrl_->ticket, s.ws, dw, am_, nullptr, stream_, &ctrl_->seed);
                 break;
             }
             default: throw std::invalid_argument("unknown resampling mode");
@@ -715,6 +789,12 @@ private:
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
     int dbg_step_ = 0, dbg_scan_ = 0;
+    double dyn_[4] = {0.0, 0.0, 0.0, 0.0};
+    cudaGraphExec_t graph_exec_ = nullptr;
+    cudaStream_t graph_stream_ = nullptr;
+    Ctrl* ctrl_stage_ = nullptr;
+    GraphKey graph_key_{}, warm_key_{};
+    bool graph_warm_ = false, capturing_ = false;
     unsigned char* slab_ = nullptr;
     size_t slab_bytes_ = 0;
     IslandInfo isl_{};

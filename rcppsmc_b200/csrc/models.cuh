@@ -56,6 +56,7 @@ struct NonlinBS {
         out[0] = shift[0] + v[0];        // mean
         out[1] = v[1] - v[0] * v[0];     // E[(x - mean)^2]; the driver reports its square root
     }
+    __device__ static __forceinline__ void load_dynamic(Params&, const double*) {}   // nothing travels through the control block
 };
 
 
@@ -104,6 +105,7 @@ struct Lineart {
         out[0] = shift[0] + v[0]; out[1] = v[1] - v[0] * v[0];   // Xm, Xv (variance, the reference takes no square root: :90-93)
         out[2] = shift[1] + v[2]; out[3] = v[3] - v[2] * v[2];   // Ym, Yv
     }
+    __device__ static __forceinline__ void load_dynamic(Params&, const double*) {}   // nothing travels through the control block
 };
 
 
@@ -141,6 +143,9 @@ struct NonlinPMMH {
     __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[1]) { h[0] = 0.0; }
     __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[1]) { f[0] = 0.0; }
     __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
+    // (sigv, sigw, log sigw) of the current proposal arrive through the control block, so one captured graph of the filter
+    // serves every MH iteration
+    __device__ static __forceinline__ void load_dynamic(Params& p, const double* m) { p.sigv = m[0]; p.sigw = m[1]; p.log_sigw = m[2]; }
 };
 
 // Scalar linear-Gaussian state space model of the conditional-SMC example: reference src/cSMCexamples.cpp:141-200.
@@ -172,6 +177,7 @@ struct LGSS {
     __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[1]) { h[0] = 0.0; }
     __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[1]) { f[0] = 0.0; }
     __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
+    __device__ static __forceinline__ void load_dynamic(Params&, const double*) {}   // nothing travels through the control block
 };
 
 

@@ -211,6 +211,7 @@ struct ScanArgs {
     const double* ustrat;     // STRATIFIED: injected uniforms U[step][0..n] (n+1 per step), or null -> Philox(seed, step)
     const long long* step_ptr;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;   // if non-null the Philox key is read from here (device scalar) instead of `seed`
     unsigned int* ticket;     // dynamic tile counter; the caller zeroes it (and the status words) before each pass
     ScanWs ws;
     AncestorMap am;
@@ -258,7 +259,7 @@ __device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long l
             else if (sure_false) p = false;
             else {
                 double U = a.ustrat ? a.ustrat[step * (nthr + 1) + j]
-                                    : u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 0).a);
+                                    : u64_to_unit(philox_draw(a.seed_ptr ? *a.seed_ptr : a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 0).a);
                 double uj = 0.0 + (inv_n - 0.0) * U;
                 p = (W - uj) > ((double)j / nd);
             }
@@ -756,14 +757,25 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_count_map(CountMapArgs 
         {
             // E[k] in the closed form used by finish_heavy_runs: E = C - k + Z with C = sum of counts before k; here the
             // counts may contain zeros that are NOT reflected in a cumulative-children value, so track E directly.
+            // Short runs are written by their own thread; a long run (a parent with many children: skewed weights right before
+            // an ESS-triggered resampling) is written by the whole warp, lane-strided, instead of one thread looping over it.
             long long Ek = E;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
-                int e = cnt[k] - 1;
-                if (e > 0) {
+                const int e = cnt[k] - 1;
+                const bool heavy = e > SURPLUS_SMALL;
+                if (e > 0 && !heavy)
                     for (int r = 0; r < e; ++r) if (Ek + r < n) a.am.surplus[Ek + r] = (uint32_t)(g0 + k);
-                    Ek += e;
+                unsigned hv = __ballot_sync(SMCB_FULL, heavy);
+                while (hv) {
+                    const int src = __ffs(hv) - 1;
+                    hv &= hv - 1u;
+                    const long long e0 = __shfl_sync(SMCB_FULL, Ek, src);
+                    const int ee = __shfl_sync(SMCB_FULL, e, src);
+                    const uint32_t par = (uint32_t)__shfl_sync(SMCB_FULL, g0 + k, src);
+                    for (int r = lane; r < ee; r += 32) if (e0 + r < n) a.am.surplus[e0 + r] = par;
                 }
+                if (e > 0) Ek += e;
             }
             E = Ek;
         }
@@ -884,6 +896,7 @@ struct DrawArgs {
     const double* uniforms;          // injected U[step][0..n), or null -> Philox(seed, step)
     const long long* step_ptr;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;   // optional device-resident Philox key (overrides `seed`)
     int* count;                      // [n] in/out: += children per parent
     uint32_t* bucket;                // [2 * nb + 2] search guide, nb = draw_buckets(n)
     int log_nb;
@@ -927,11 +940,12 @@ static __global__ void __launch_bounds__(256) k_multinomial_draw(DrawArgs a) {
     const long long ndraws = a.floor_total ? n - (long long)*a.floor_total : n;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
     const unsigned long long Q = a.cum[n - 1];
+    const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     const int s = draw_bucket_shift(Q, a.log_nb);
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ndraws; j += (long long)gridDim.x * blockDim.x) {
         unsigned long long m;
         if (a.uniforms) m = (unsigned long long)(a.uniforms[step * n + j] * 9007199254740992.0);
-        else m = philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 2).a >> 11;
+        else m = philox_draw(seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)j, 2).a >> 11;
         // t = floor(m Q / 2^53)
         unsigned long long hi = __umul64hi(m, Q), lo = m * Q;
         unsigned long long t = (hi << 11) | (lo >> 53);
@@ -968,7 +982,7 @@ template <int SRC>
 inline void launch_resample_draws(int mode, const double* in, long long n, const double* lse_ptr, const int* enable_ptr,
                                   const double* uniforms, const long long* step_ptr, unsigned long long seed,
                                   unsigned int* ticket, const ScanWs& ws, const DrawWs& dw, const AncestorMap& am,
-                                  unsigned int* tail_info, cudaStream_t stream) {
+                                  unsigned int* tail_info, cudaStream_t stream, const unsigned long long* seed_ptr = nullptr) {
     static int grid_cum = 0, grid_map = 0, grid_draw = 0;
     if (!grid_cum) {
         int dev = 0, sms = 0, b = 0;
@@ -990,7 +1004,7 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
     SMCB_CUDA(cudaGetLastError());
     DrawArgs d{};
     d.cum = dw.cum; d.n = n; d.enable_ptr = enable_ptr; d.floor_total = mode == RESIDUAL ? dw.floor_total : nullptr;
-    d.uniforms = uniforms; d.step_ptr = step_ptr; d.seed = seed; d.count = dw.count;
+    d.uniforms = uniforms; d.step_ptr = step_ptr; d.seed = seed; d.seed_ptr = seed_ptr; d.count = dw.count;
     d.bucket = dw.bucket; d.log_nb = draw_log_buckets(n);
     long long need = ((2LL << d.log_nb) + 2 + 255) / 256;
     k_draw_buckets<<<(int)(need < grid_draw ? need : grid_draw), 256, 0, stream>>>(d);

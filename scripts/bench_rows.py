@@ -81,12 +81,12 @@ if have_ref:
 rows.append(row)
 
 # ---- nonLinPMMH: 2^16-particle filters over 500 observations (BASELINE configs[3]) -----------------------------------------
-T, N, M = 500, 1 << 16, 20
+T, N, M = 500, 1 << 16, 200
 y = H.sim_nonlin(T, 7, var_init=5.0, cos_offset=0.0)[1]
-t = best_of(lambda: smc.nonLinPMMH(y, N, M, seed=9), reps=2)
-row = {"row": "nonLinPMMH", "config": "2^16-particle filters x 500 observations, 20 MH iterations (21 filters), multinomial / 0.5, one chain", "gpu_seconds": t,
+t = best_of(lambda: smc.nonLinPMMH(y, N, M, seed=9), reps=1)
+row = {"row": "nonLinPMMH", "config": "2^16-particle filters x 500 observations, 200 MH iterations (201 filters), multinomial / 0.5, one chain", "gpu_seconds": t,
        "filters_per_s": (M + 1) / t, "particle_steps_per_s": (M + 1) * N * T / t,
-       "note": "launch/latency bound at this filter size (4 launches per step of 65536 particles); chains shard one per GPU"}
+       "note": "each filter is one replay of a captured CUDA graph (4 kernels per step); ~0.26 s one-off capture cost included; chains shard one per GPU"}
 if have_ref:
     tc = cpu_time(lambda: H.r_pmmh(y, 1 << 13, 2, 3))
     row["cpu_reference"] = {"particle_steps_per_s": 3 * (1 << 13) * T / tc, "cores": 1, "sample": f"2^13-particle filters x 500 obs, 3 filters, {tc:.1f} s"}

@@ -67,3 +67,14 @@ def test_native_chain_moves_towards_the_posterior_and_reports_progress(smc):
     assert out["loglike"][-1] > out["loglike"][0]
     again = smc.nonLinPMMH(y, 1000, 20, seed=5)
     assert np.array_equal(again["samples_sigv"], out["samples_sigv"][:21])   # deterministic given the seed
+
+
+def test_graph_replayed_filters_reproduce_the_eager_chain(smc):
+    # chains of >= 64 iterations replay one captured CUDA graph per inner filter (seed and proposal travel through the
+    # control block); a short chain runs the same filters eagerly: the common prefix must be bit-identical
+    y = _data(40, 5)
+    short = smc.nonLinPMMH(y, 3000, 20, seed=11)
+    long = smc.nonLinPMMH(y, 3000, 80, seed=11)
+    for k in ("samples_sigv", "samples_sigw", "loglike", "logprior", "MH_acceptance_rate"):
+        assert np.array_equal(long[k][:21], short[k]), k
+    assert len(np.unique(long["loglike"])) > 5
