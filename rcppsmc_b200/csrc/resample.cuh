@@ -236,10 +236,14 @@ __device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long l
                                              double dRand, long long step) {
     if (MODE == SYSTEMATIC) {
         if (POW2) {
-            double g = fmin(fmax((W - dRand) * nd, 0.0), nd);   // exact scaling; clamp to [0, N]
-            double t = g + TWO52;                                // round to nearest integer (low word of t)
-            double r = t - TWO52;
-            return __double2loint(t) + (r < g ? 1 : 0);          // ceil
+            // ceil((W - u) N) clamped to [0, N].  The scaling is exact; adding 1.5 * 2^52 rounds to the nearest integer and leaves
+            // it, in two's complement, in the low word (valid for |g| < 2^31: g > -1 and N <= 2^30 here), so the clamps are two
+            // integer min/max instead of two fp64 ones.
+            const double g = (W - dRand) * nd;
+            const double t = g + 6755399441055744.0;
+            const double r = t - 6755399441055744.0;
+            const int c = __double2loint(t) + (r < g ? 1 : 0);
+            return min(max(c, 0), (int)nthr);
         }
         return (int)children_below(W - dRand, nthr, nd, false);
     } else {
