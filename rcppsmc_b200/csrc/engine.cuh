@@ -144,9 +144,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     //   stage A (pair p+3S)  bitmap word + rank base          stage B (pair p+2S)  rank -> surplus loads
     //   stage C (pair p+S)   parent state (and stored log-weight when the last step did not resample)
     //   compute (pair p)     moments, RNG, model functor, stores, online log-sum-exp
-    const long long npairs = (n + 1) >> 1;
-    const long long stride = (long long)gridDim.x * STEP_THREADS;
-    const long long p0 = (long long)blockIdx.x * STEP_THREADS + tid;
+    // 32-bit pair / slot indices inside the loop (n < 2^31): half the integer work of 64-bit index arithmetic
+    const uint32_t n32 = (uint32_t)n;
+    const uint32_t npairs = (uint32_t)((n + 1) >> 1);
+    const uint32_t stride = gridDim.x * STEP_THREADS;
+    const uint32_t p0 = blockIdx.x * STEP_THREADS + tid;
     // Every link lands in shared memory through cp.async (each thread owns one slot per array and is the only reader of it, so
     // no barrier is involved).  Measured with ncu, a register-destination version of this pipeline stalled on the scoreboards
     // of freshly issued gathers whenever a register of an older, finished load was recycled.  In island mode the source of a
@@ -167,20 +169,20 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     const uint32_t slot_lo = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;
     uint32_t zfB = 0u, selfB = 0u;             // stage B result: bit h = slot h takes its surplus entry, bit 2+h = slot h takes particle 0
     double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result, read back from shared memory
-    auto stageA = [&](long long p) {
+    auto stageA = [&](uint32_t p) {
         if (ASYNC && decode && p < npairs) {
             cp_async4(sa_mk, a.am.zmask + (p >> 4));
             cp_async4(sa_mk + ST4, a.am.zbase + (p >> 4));
         }
     };
-    auto stageB = [&](long long p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
+    auto stageB = [&](uint32_t p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
         if (ASYNC && p < npairs) {
-            const long long s0 = 2 * p;
-            selfB = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc + s0) : (uint32_t)s0;   // global slot id
+            const uint32_t s0 = 2u * p;
+            selfB = ISLAND ? slot_lo + s0 : s0;   // global slot id
             zfB = 0u;
             if (decode) {
                 const uint32_t mA = s_mk[0][tid], bA = s_mk[1][tid];
-                const uint32_t bit = (uint32_t)s0 & 31u;
+                const uint32_t bit = s0 & 31u;
                 const uint32_t below = mA & ((1u << bit) - 1u);
                 const uint32_t rank = bA + __popc(below);
                 const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
@@ -212,10 +214,10 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
         }
     };
-    auto stageC = [&](long long p) {   // consumes the surplus entries fetched for this p one iteration ago
+    auto stageC = [&](uint32_t p) {   // consumes the surplus entries fetched for this p one iteration ago
         if (ASYNC && p < npairs) {
-            const long long s0 = 2 * p;
-            const bool has1 = s0 + 1 < n;
+            const uint32_t s0 = 2u * p;
+            const bool has1 = s0 + 1u < n32;
             uint32_t anc[2];
             anc[0] = (zfB & 1u) ? s_sp[0][tid] : ((zfB & 4u) ? 0u : selfB);
             anc[1] = (zfB & 2u) ? s_sp[1][tid] : ((zfB & 8u) ? 0u : selfB + 1u);
@@ -255,9 +257,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         stageC(p0); stageB(p0 + stride); stageA(p0 + 2 * stride); cp_async_commit();
     }
 
-    for (long long p = p0; p < npairs; p += stride) {
-        const long long s0 = 2 * p;
-        const bool has1 = s0 + 1 < n;
+    for (uint32_t p = p0; p < npairs; p += stride) {
+        const uint32_t s0 = 2u * p;
+        const bool has1 = s0 + 1u < n32;
         double x[2][D], lwv[2];
         if (PHASE != PHASE_INIT) {
             if (ASYNC) {   // everything issued one iteration ago has had a whole iteration to land
@@ -297,8 +299,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 long long off = PHASE == PHASE_INIT ? 0 : n * Model::NZ_INIT + (tcur - 1) * n * Model::NZ_MOVE;
 #pragma unroll
                 for (int k = 0; k < NZ; ++k) {
-                    z[0][k] = a.znoise[off + s0 * NZ + k];
-                    z[1][k] = has1 ? a.znoise[off + (s0 + 1) * NZ + k] : 0.0;
+                    z[0][k] = a.znoise[off + (long long)s0 * NZ + k];
+                    z[1][k] = has1 ? a.znoise[off + ((long long)s0 + 1) * NZ + k] : 0.0;
                 }
             } else {
 #pragma unroll
