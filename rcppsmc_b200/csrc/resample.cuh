@@ -277,9 +277,12 @@ __device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long l
 // are written by the owning lane; longer ones are finished by the whole warp (write_surplus_heavy, cold path,
 // 16-byte stores for the aligned middle of very long runs).
 constexpr int SURPLUS_SMALL = 8;
-__device__ __forceinline__ void write_surplus_small(uint32_t* __restrict__ surplus, long long E, int e, uint32_t gk, long long cap) {
-    const int small = e < SURPLUS_SMALL ? e : SURPLUS_SMALL;
-    for (int r = 0; r < small; ++r) if (E + r < cap) surplus[E + r] = gk;
+__device__ __forceinline__ void write_surplus_small(uint32_t* __restrict__ surplus, int E, int e, uint32_t gk, int cap) {
+    int m = e < SURPLUS_SMALL ? e : SURPLUS_SMALL;
+    const int room = cap - E;              // list positions are < 2^31: 32-bit arithmetic, one address computation
+    m = m < room ? m : room;
+    uint32_t* p = surplus + E;
+    for (int r = 0; r < m; ++r) p[r] = gk;
 }
 static __device__ __noinline__ void write_surplus_heavy(uint32_t* __restrict__ surplus, long long hE, long long hend, uint32_t hk, long long cap) {
     const int lane = threadIdx.x & 31;
@@ -365,6 +368,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
     const double mass0 = ISLAND ? u64_to_double_exact(*a.mass_offset_ptr) * INV_TWO52 : 0.0;   // weight mass of lower ranks
     const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
     const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
+    const int n32 = (int)n;                                // n < 2^31
     // children handed out before this rank's first slot (0 on a single GPU)
     const int cstart = ISLAND ? children_upto<MODE, POW2>(mass0, a, nthr, nd, inv_n, dRand, step) : 0;
 
@@ -375,10 +379,11 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
         if (t >= 0) {
             const long long base = (long long)t * SCAN_TILE;
             const bool full = base + SCAN_TILE <= n;
+            const int left = full ? SCAN_TILE : (int)(n - base);   // valid slots of this tile
 #pragma unroll
             for (int r = 0; r < SCAN_ITEMS; ++r) {
                 const int i = r * SCAN_THREADS + tid;
-                if (full || base + i < n) {
+                if (i < left) {
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa_stage + (unsigned)(r * SCAN_THREADS * 8)), "l"(a.in + base + i) : "memory");
                 }
             }
@@ -405,6 +410,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
         if (t1 >= 0) {
             const long long base = (long long)t1 * SCAN_TILE;
             const bool full = base + SCAN_TILE <= n;
+            const int left = full ? SCAN_TILE : (int)(n - base);   // valid slots of this tile
             double* sq = S.cum[b1];
             double raw[SCAN_ITEMS];
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -415,7 +421,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
             for (int r = 0; r < SCAN_ITEMS; ++r) {
                 const int i = r * SCAN_THREADS + tid;
                 double q = 0.0;
-                if (full || base + i < n) {
+                if (i < left) {
                     const double w = (SRC == SRC_LOGW) ? fm_exp(raw[r] - lse) : raw[r];
                     q = (w + 1.0) - 1.0;                  // round to the 2^-52 grid (ulp of [1,2))
                 }
@@ -519,7 +525,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
                 for (int k = 0; k < SCAN_ITEMS; ++k) {
                     int ck = sc[tid * (SCAN_ITEMS + 1) + k];
                     cnt[k] = ck - cp;
-                    if (cnt[k] == 0 && (full || (long long)g0 + k < n)) zbits |= 1u << k;
+                    if (cnt[k] == 0 && (full || g0 + k < n32)) zbits |= 1u << k;
                     cp = ck;
                 }
             }
@@ -528,7 +534,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
                 unsigned m = zbits << (8 * (lane & 3));
                 m |= __shfl_xor_sync(SMCB_FULL, m, 1);
                 m |= __shfl_xor_sync(SMCB_FULL, m, 2);
-                if ((lane & 3) == 0 && (full || (long long)g0 < n)) {
+                if ((lane & 3) == 0 && (full || g0 < n32)) {
                     a.am.zmask[g0 >> 5] = m;
                     a.am.zbase[g0 >> 5] = (uint32_t)zexcl;
                 }
@@ -539,7 +545,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
 #pragma unroll
                 for (int k = 0; k < SCAN_ITEMS; ++k) {
                     const int e = cnt[k] - 1;
-                    write_surplus_small(a.am.surplus, E, e, gslot0 + (uint32_t)(g0 + k), scap);
+                    write_surplus_small(a.am.surplus, E, e, gslot0 + (uint32_t)(g0 + k), (int)scap);
                     if (e > SURPLUS_SMALL) hbits |= 1u << k;
                     E += cnt[k] - 1 + (int)((zbits >> k) & 1u);      // E[k+1] = E[k] + count[k] - 1 + z[k]
                 }
