@@ -26,7 +26,7 @@ namespace smcb {
 #endif
 constexpr int SCAN_THREADS = SMCB_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 slots per tile
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 1024 slots per tile
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
 constexpr unsigned long long ST_AGG = 1ull << 62;
@@ -329,11 +329,12 @@ __device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus
 
 inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 
-// One pass: weights -> (zmask, zbase, surplus).  Persistent blocks pull 2048-slot tiles from a ticket counter and keep
-// THREE tiles in flight, one per pipeline stage, so that neither look-back chain is ever waited on right after its
+// One pass: weights -> (zmask, zbase, surplus).  Persistent blocks pull 1024-slot tiles from a ticket counter and keep
+// FOUR tiles in flight, one per pipeline stage, so that neither look-back chain is ever waited on right after its
 // aggregate was published (measured: un-pipelined, each look-back stalled ~10k cycles on predecessors that had not
-// reached their publish point yet):
-//   S1(tile t+2)  coalesced load, quantise to the 2^-52 grid, block scan, publish the weight-mass aggregate
+// reached their publish point yet) and the input never sits on the critical path:
+//   S0(tile t+3)  cp.async of the tile's input into shared memory (each thread stages the slots it will read)
+//   S1(tile t+2)  staged input -> registers, quantise to the 2^-52 grid, block scan, publish the weight-mass aggregate
 //   S2(tile t+1)  look-back A (published a full iteration ago) -> children counts -> publish the zero-slot aggregate
 //   S3(tile t)    look-back B (published a full iteration ago) -> zero-slot bitmap + surplus lists
 // Stage state lives in shared memory (double-buffered), not registers.
