@@ -12,6 +12,7 @@
 // in order on shared index state.  Every conditional resampling scheme is "scan, then one independent binary search per
 // offspring" (the reference walks the cumulative weights sequentially, O(N^2) worst case through arma::find(tail...)).
 #include <cmath>
+#include <functional>
 #include <vector>
 
 #include "cabi_common.cuh"
@@ -287,7 +288,8 @@ LGSS::Params lgss_params(const double* y_dev, double phi, double var_evol, doubl
 
 void run_chains(const double* y_host, long T, long particles, double phi, double var_evol, double x0, double var_obs, long n_chains,
                 long runs_per_chain, const int* modes_host, const double* ref_host, uint64_t seed, const double* noise_host,
-                const double* unif_host, double* lognc, uint32_t* refidx_out, uint32_t* anc_out, double* val_out, double* lw_out, int* res_out) {
+                const double* unif_host, double* lognc, uint32_t* refidx_out, uint32_t* anc_out, double* val_out, double* lw_out, int* res_out,
+                const std::function<void()>& overlap = nullptr) {
     if (!y_host || T < 2 || particles < 2 || n_chains < 1 || runs_per_chain < 1 || !modes_host || !ref_host || !lognc)
         throw std::invalid_argument("conditionalBPF: need data with T >= 2, particles >= 2, chains, modes, reference trajectories and an output");
     if (particles >= (1LL << 31)) throw std::invalid_argument("conditionalBPF: particles must be < 2^31");
@@ -321,9 +323,22 @@ void run_chains(const double* y_host, long T, long particles, double phi, double
     a.L = Lb.as<int>(); a.anc = ancb.as<uint32_t>(); a.refidx = ridx.as<uint32_t>();
     a.lognc = d_nc.as<double>(); a.refidx_out = d_ro.as<uint32_t>();
     a.anc_out = d_anc.as<uint32_t>(); a.val_out = d_val.as<double>(); a.lw_out = d_lw.as<double>(); a.res_out = d_res.as<int>();
-    k_csmc_chain<<<(unsigned)n_chains, CS_THREADS>>>(a);
-    SMCB_CUDA(cudaGetLastError());
-    SMCB_CUDA(cudaDeviceSynchronize());
+    // The chains run on their own non-blocking stream: independent work handed in by the caller (the plain filters of
+    // compareNCestimates, which use the legacy stream) overlaps with them instead of queueing behind one long kernel.
+    cudaStream_t cs = nullptr;
+    SMCB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    k_csmc_chain<<<(unsigned)n_chains, CS_THREADS, 0, cs>>>(a);
+    cudaError_t le = cudaGetLastError();
+    try {
+        if (le == cudaSuccess && overlap) overlap();
+    } catch (...) {
+        cudaStreamSynchronize(cs); cudaStreamDestroy(cs);
+        throw;
+    }
+    cudaError_t se = cudaStreamSynchronize(cs);
+    cudaStreamDestroy(cs);
+    SMCB_CUDA(le);
+    SMCB_CUDA(se);
     SMCB_CUDA(cudaMemcpy(lognc, d_nc.p, sizeof(double) * runs, cudaMemcpyDeviceToHost));
     if (refidx_out) SMCB_CUDA(cudaMemcpy(refidx_out, d_ro.p, sizeof(uint32_t) * runs * T, cudaMemcpyDeviceToHost));
     if (anc_out) SMCB_CUDA(cudaMemcpy(anc_out, d_anc.p, sizeof(uint32_t) * hist, cudaMemcpyDeviceToHost));
@@ -398,13 +413,6 @@ extern "C" int smcb200_compareNCestimates(const double* data_host, long T, long 
             throw std::invalid_argument("compareNCestimates: data (T >= 2), particles >= 2, simNum >= 1, referenceTraj and both outputs required");
         require_device();
         const int order[4] = {SMCB200_MULTINOMIAL, SMCB200_RESIDUAL, SMCB200_STRATIFIED, SMCB200_SYSTEMATIC};   // cSMCexamples.cpp:82-125
-        // plain bootstrap filters: column c of smcOut is order[c]
-        PlainLgss f(data_host, T, particles, seed);
-        f.allow_graph = simNum >= 16;
-        for (int c = 0; c < 4; ++c)          // scheme-major: one captured graph per scheme serves all simulations
-            for (int i = 0; i < simNum; ++i)
-                smcOut_host[(size_t)c * simNum + i] =
-                    f.run(order[c], phi, varStateEvol, stateInit, varObs, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(4 * i + c + 1), nullptr, nullptr);
         // conditional filters: run (i, c) uses referenceTraj.col(i); one chain reproduces the reference's single sampler object
         const long runs = 4L * simNum;
         std::vector<int> modes(runs);
@@ -414,8 +422,23 @@ extern "C" int smcb200_compareNCestimates(const double* data_host, long T, long 
                 modes[4 * i + c] = order[c];
                 for (long t = 0; t < T; ++t) ref[(size_t)(4 * i + c) * T + t] = referenceTraj_host[(size_t)i * T + t];
             }
-        run_chains(data_host, T, particles, phi, varStateEvol, stateInit, varObs, independent_sims ? simNum : 1, independent_sims ? 4 : runs,
-                   modes.data(), ref.data(), seed ^ 0xC5A3C5A3C5A3C5A3ull, nullptr, nullptr, nc.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+        // plain bootstrap filters (column c of smcOut is order[c]) run while the chains are in flight
+        auto plain = [&]() {
+            PlainLgss f(data_host, T, particles, seed);
+            f.allow_graph = simNum >= 16;
+            for (int c = 0; c < 4; ++c)          // scheme-major: one captured graph per scheme serves all simulations
+                for (int i = 0; i < simNum; ++i)
+                    smcOut_host[(size_t)c * simNum + i] =
+                        f.run(order[c], phi, varStateEvol, stateInit, varObs, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(4 * i + c + 1), nullptr, nullptr);
+        };
+        // a single chain occupies one SM for the whole call: the plain filters overlap with it; many chains fill the GPU, so the
+        // plain filters follow them instead of competing for the same SMs
+        const long n_chains = independent_sims ? simNum : 1;
+        const bool overlap = n_chains <= 8;
+        run_chains(data_host, T, particles, phi, varStateEvol, stateInit, varObs, n_chains, runs / n_chains, modes.data(), ref.data(),
+                   seed ^ 0xC5A3C5A3C5A3C5A3ull, nullptr, nullptr, nc.data(), nullptr, nullptr, nullptr, nullptr, nullptr,
+                   overlap ? std::function<void()>(plain) : std::function<void()>());
+        if (!overlap) plain();
         for (int i = 0; i < simNum; ++i)
             for (int c = 0; c < 4; ++c) csmcOut_host[(size_t)c * simNum + i] = nc[4 * i + c];
         return SMCB200_OK;
