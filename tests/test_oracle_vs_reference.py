@@ -198,3 +198,30 @@ def test_plain_lgss_filter_bit_exact(mode):
     v, flags = H.o_bpf_lgss(y, N, mode, LGSS_PAR, z, U, want_flags=True)
     assert flags.sum() >= 3
     assert v == H.r_bpf_lgss(mode, z, U[flags == 1].reshape(-1))
+
+
+def test_randomised_configurations_blockpf_and_conditional_chain():
+    # breadth: many small random shapes (odd N, short series, lag >= T, every scheme order) stay bit-identical
+    rng = np.random.default_rng(2026)
+    for _ in range(40):
+        N, T, lag = int(rng.integers(2, 90)), int(rng.integers(1, 25)), int(rng.integers(1, 12))
+        y = H.sim_lg(T, int(rng.integers(1 << 30)), float(rng.uniform(1.0, 30.0)))
+        z, U = rng.standard_normal((T, lag, N)), rng.random(T)
+        o = H.o_blockpf(y, N, lag, z, U)
+        r = H.r_blockpf(y, N, lag, z, U[o["resampled"] == 1])
+        assert o["logNC"] == r["logNC"] and np.array_equal(o["values"], r["values"]) and np.array_equal(o["weight"], r["weight"]), (N, T, lag)
+    for _ in range(15):
+        N, T = int(rng.integers(8, 70)), int(rng.integers(3, 20))
+        par = (float(rng.uniform(0.5, 0.99)), float(rng.uniform(0.3, 2.0)), float(rng.normal()), float(rng.uniform(0.3, 2.0)))
+        x, y = H.sim_lgss(T, int(rng.integers(1 << 30)), par[0], par[1], par[3], par[2])
+        H.r_csmc_open(y, N, par)
+        refidx = np.zeros(T, dtype=np.uint32)
+        for mode in rng.permutation([H.MULTINOMIAL, H.RESIDUAL, H.STRATIFIED, H.SYSTEMATIC, H.RESIDUAL, H.SYSTEMATIC]):
+            mode = int(mode)
+            reft = x + rng.standard_normal(T)
+            z, U = rng.standard_normal((T, N)), rng.random((T, N + 2))
+            o = H.o_csmc_run(y, N, mode, par, reft, refidx, z, U)
+            r = H.r_csmc_run(mode, reft, T, N, z, H.csmc_uniform_queue(mode, U, o, N))
+            assert o["logNC"] == r["logNC"], (N, T, mode)
+            for key in ("ancestors", "values", "logw", "refidx", "resampled"):
+                assert np.array_equal(o[key], r[key]), (N, T, mode, key)
