@@ -225,3 +225,24 @@ def test_randomised_configurations_blockpf_and_conditional_chain():
             assert o["logNC"] == r["logNC"], (N, T, mode)
             for key in ("ancestors", "values", "logw", "refidx", "resampled"):
                 assert np.array_equal(o[key], r[key]), (N, T, mode, key)
+
+
+def test_randomised_configurations_filters():
+    # breadth for the two bootstrap filters: random sizes, thresholds on both sides of 1, both exact-parity schemes
+    rng = np.random.default_rng(77)
+    for k in range(24):
+        N, T = int(rng.integers(1, 400)), int(rng.integers(1, 30))
+        mode = H.SYSTEMATIC if k % 2 else H.STRATIFIED
+        thr = float(rng.choice([0.3, 0.5, 0.9, 1.01 * N, 0.75 * N]))
+        z, U = rng.standard_normal(4 * N * T), rng.random(T * (N + 1))
+        if k % 3:
+            _, y = H.sim_nonlin(T, int(rng.integers(1 << 30)))
+            r, o = H.r_pfnonlinbs(y, N, mode, thr, z[:N * T], U), H.o_pfnonlinbs(y, N, mode, thr, z=z[:N * T], U=U)
+            keys = ("mean", "sd", "logNC")
+        else:
+            data = H.sim_lineart(T, int(rng.integers(1 << 30)))
+            r, o = H.r_pflineart(data, N, mode, thr, z, U), H.o_pflineart(data, N, mode, thr, z=z, U=U)
+            keys = ("Xm", "Xv", "Ym", "Yv", "logNC")
+        assert np.array_equal(r["resampled"], o["resampled"]), (k, N, T, mode, thr)
+        for key in keys:
+            assert np.array_equal(r[key], o[key]), (k, N, T, mode, thr, key)
