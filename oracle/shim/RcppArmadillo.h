@@ -374,6 +374,7 @@ template <class T> struct Vector_ {
     Vector_(int n) : v(n) {}
     Vector_(unsigned long n) : v(n) {}
     Vector_(const std::vector<T>& o) : v(o) {}
+    Vector_(const T* first, const T* last) : v(first, last) {}   // iterator-range constructor (glue syntax check)
     Vector_(long n, T fill) : v(n, fill) {}
     Vector_(unsigned long n, T fill) : v(n, fill) {}
     template <class U> Vector_(const arma::Col<U>& o) : v(o.d.begin(), o.d.end()) {}

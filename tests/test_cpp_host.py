@@ -51,3 +51,16 @@ def test_cpp_host_matches_the_python_mirror():
     c = smc.compareNCestimates(y, 200, 2, (0.9, 1.0, 0.0, 1.0), np.zeros((24, 2)), seed=1)
     assert float(lines["compareNCestimates"][2]) == c["smcOut"][0, 0] and float(lines["compareNCestimates"][4]) == c["csmcOut"][0, 0]
     assert lines["argument"][-1] == "1"
+
+
+def test_rcpp_glue_is_well_formed_against_the_stand_in_headers():
+    # glue/smcb200_rcpp_glue.cpp holds the eight [[Rcpp::export]] bodies a maintainer drops into the R package.  R / Rcpp /
+    # Armadillo are absent here, so this is a syntax / type check against oracle/shim's stand-ins, not a real Rcpp build.
+    src = os.path.join(ROOT, "glue", "smcb200_rcpp_glue.cpp")
+    text = open(src).read()
+    for name in ("pfNonlinBS_impl", "pfLineartBS_impl", "LinReg_impl", "LinRegLA_impl", "LinRegLA_adapt_impl", "blockpfGaussianOpt_impl",
+                 "nonLinPMMH_impl", "compareNCestimates_imp"):
+        assert text.count("[[Rcpp::export]]") == 8 and (" " + name + "(") in text, name
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
