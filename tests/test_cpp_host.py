@@ -60,7 +60,7 @@ def test_rcpp_glue_is_well_formed_against_the_stand_in_headers():
     text = open(src).read()
     for name in ("pfNonlinBS_impl", "pfLineartBS_impl", "LinReg_impl", "LinRegLA_impl", "LinRegLA_adapt_impl", "blockpfGaussianOpt_impl",
                  "nonLinPMMH_impl", "compareNCestimates_imp"):
-        assert text.count("[[Rcpp::export]]") == 8 and (" " + name + "(") in text, name
+        assert text.count("// [[Rcpp::export]]\n") == 8 and (" " + name + "(") in text, name
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), src],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
