@@ -37,5 +37,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """Experiment builds (kernel A/B measurements): build/libsmcb200_<name>.so with extra -D switches; loaded via SMCB200_LIB."""
+    out_dir = os.path.join(ROOT, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libsmcb200_{name}.so")
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SOURCES
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed building {out}")
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

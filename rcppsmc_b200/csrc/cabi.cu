@@ -188,17 +188,23 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
             ScanArgs a{};
             a.in = w.as<double>(); a.n = n; a.n_glob = n; a.u_ptr = u_dev; a.ticket = ticket; a.ws = ws; a.am = am;
             a.count_out = counts.as<int>(); a.tail_info = tail;
+            DevBuf cslot(sizeof(uint32_t) * resample_cslot_entries(n));
+            a.cslot = cslot.as<uint32_t>();
+            const char* impl_env = getenv("SMCB200_SCAN_IMPL");
+            const bool old_impl = impl_env && atoi(impl_env) == 0;   // block-tiled kernel, kept for A/B measurements
             DevBuf us;
             if (mode == SMCB200_SYSTEMATIC) {
                 if (!uniforms_host || n_uniforms < 1) throw std::invalid_argument("smcb200_resample: SYSTEMATIC needs 1 uniform");
                 SMCB_CUDA(cudaMemcpy(u_dev, uniforms_host, sizeof(double), cudaMemcpyHostToDevice));
-                launch_resample_scan<SRC_WEIGHTS, SYSTEMATIC>(a, 0);
+                if (old_impl) launch_resample_scan<SRC_WEIGHTS, SYSTEMATIC>(a, 0);
+                else launch_resample_passes<SRC_WEIGHTS, SYSTEMATIC>(a, 0);
             } else if (mode == SMCB200_STRATIFIED) {
                 if (!uniforms_host || n_uniforms < n + 1) throw std::invalid_argument("smcb200_resample: STRATIFIED needs n+1 uniforms");
                 us = DevBuf(sizeof(double) * (n + 1));
                 SMCB_CUDA(cudaMemcpy(us.p, uniforms_host, sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
                 a.ustrat = us.as<double>();
-                launch_resample_scan<SRC_WEIGHTS, STRATIFIED>(a, 0);
+                if (old_impl) launch_resample_scan<SRC_WEIGHTS, STRATIFIED>(a, 0);
+                else launch_resample_passes<SRC_WEIGHTS, STRATIFIED>(a, 0);
             } else {
                 if (!uniforms_host || n_uniforms < n) throw std::invalid_argument("smcb200_resample: MULTINOMIAL / RESIDUAL need n uniforms");
                 us = DevBuf(sizeof(double) * n);

@@ -220,11 +220,13 @@ void run_blockpf(const double* y_host, long T, long particles, long lag, uint64_
     sc.step_ptr = &a.ctrl->T; sc.seed = seed; sc.ticket = &a.ctrl->ticket;
     sc.ws = ScanWs{status.as<unsigned long long>(), status.as<unsigned long long>() + ntiles, status.as<unsigned long long>() + 2 * ntiles};
     sc.am = am; sc.n_glob = n;
+    DevBuf cslot(sizeof(uint32_t) * resample_cslot_entries(n));
+    sc.cslot = cslot.as<uint32_t>();
     for (long t = 0; t < T; ++t) {
         if (t == 0) k_bpf_step<true><<<grid, 256, 0, st>>>(a);
         else k_bpf_step<false><<<grid, 256, 0, st>>>(a);
         SMCB_CUDA(cudaMemsetAsync(status.p, 0, sizeof(unsigned long long) * 3 * ntiles, st));
-        launch_resample_scan<SRC_LOGW, SYSTEMATIC>(sc, st);
+        launch_resample_passes<SRC_LOGW, SYSTEMATIC>(sc, st);
         k_bpf_decode<<<grid, 256, 0, st>>>(a, am);
         SMCB_CUDA(cudaGetLastError());
     }

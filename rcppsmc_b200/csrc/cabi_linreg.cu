@@ -104,6 +104,8 @@ long run_la(bool adaptive, const double* data_host, long n_obs, const double* te
     sc.ticket = &a.ctrl->ticket;
     sc.ws = ScanWs{status.as<unsigned long long>(), status.as<unsigned long long>() + ntiles, status.as<unsigned long long>() + 2 * ntiles};
     sc.am = a.am;
+    DevBuf cslot(sizeof(uint32_t) * resample_cslot_entries(n));
+    sc.cslot = cslot.as<uint32_t>();
 
     long L = 0;
     for (long g = 0;; ++g) {
@@ -139,7 +141,7 @@ long run_la(bool adaptive, const double* data_host, long n_obs, const double* te
         }
         k_la_pre_resample<<<1, 1, 0, st>>>(a);
         SMCB_CUDA(cudaMemsetAsync(status.p, 0, sizeof(unsigned long long) * 3 * ntiles, st));
-        launch_resample_scan<SRC_LOGW, SYSTEMATIC>(sc, st);
+        launch_resample_passes<SRC_LOGW, SYSTEMATIC>(sc, st);
         k_la_mcmc<<<grid_mcmc, 128, 0, st>>>(a);
         SMCB_CUDA(cudaGetLastError());
         L = g + 1;

@@ -92,4 +92,34 @@ struct LseAcc {
     }
 };
 
+// Sums of weights exp(lw - c) against a shift c that is common to the whole step: s = sum e, q = sum e^2, g_j = sum e h_j, and
+// the running maximum of lw (which validates c afterwards and predicts the next one).  One exp per element, no selects; the
+// exponential is returned so that the caller can store it -- the resampling scan then normalises with one multiplication
+// instead of a second exp.  logNC increment = c + log s (population.h:46-50), ESS = s^2 / q (sampler.h:413-417).
+template <int G>
+struct WAcc {
+    double s, q, mx;
+    double g[G > 0 ? G : 1];
+    __device__ __forceinline__ void clear() {
+        s = 0.0; q = 0.0; mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < G; ++j) g[j] = 0.0;
+    }
+    __device__ __forceinline__ double add(double lw, double c, const double* h) {
+        double e = fm_exp(lw - c);          // 0 for lw = -inf
+        e = (lw == lw) ? e : lw;            // a NaN log-weight poisons the sums, as it does in the reference
+        s += e;
+        q = fma(e, e, q);
+#pragma unroll
+        for (int j = 0; j < G; ++j) g[j] = fma(e, h[j], g[j]);
+        mx = fmax(mx, lw);
+        return e;
+    }
+    __device__ __forceinline__ void warp_reduce() {
+        s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx);
+#pragma unroll
+        for (int j = 0; j < G; ++j) g[j] = warp_sum(g[j]);
+    }
+};
+
 }  // namespace smcb

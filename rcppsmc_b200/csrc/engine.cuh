@@ -46,6 +46,9 @@ struct Ctrl {
     double u_res;           // base uniform in [0,1) for the current step's resampling
     double thr;             // dResampleThreshold (absolute)
     double log_n;           // log(N)
+    double cshift;          // shift c of the stored weights exp(lw - c): predicted for the NEXT k_step by the previous one
+    double cbase;           // level of the log-weights before the next step's increment (-log N after resampling)
+    double inv_s;           // 1 / sum of the stored shifted weights (the scan normalises with one multiplication)
     double shift[MAX_SHIFT];  // centring constants for the fused moment pass (pre-resample weighted means)
     int resampled;          // nResampled: ancestor map is pending for the next gather
     int parity;             // which state buffer holds the current population
@@ -56,8 +59,8 @@ struct Ctrl {
     unsigned long long floor_total;  // RESIDUAL: deterministic children handed out this step
     // island mode (one rank of a partitioned population)
     unsigned long long mass_offset;  // integer weight mass of all lower ranks (start of this rank's cumulative scan)
-    long long zoff[ISL_MAX + 1];     // zero-count slots before each rank (exclusive prefix; [world] = total)
-    long long eoff[ISL_MAX + 1];     // surplus-list entries before each rank
+    long long zoff[ISL_MAX + 2];     // zero-count slots before each rank (exclusive prefix; [world] = total; [ISL_MAX+1] = this rank's own)
+    long long eoff[ISL_MAX + 2];     // surplus-list entries before each rank (same layout)
     // what may change between two filters of the same shape (so that a captured CUDA graph of the filter can be replayed):
     unsigned long long seed;         // Philox key of this run
     double mparam[4];                // model parameters picked up by Model::load_dynamic (e.g. the PMMH proposal)
@@ -75,6 +78,7 @@ struct StepArgs {
     double* xa[Model::D];
     double* xb[Model::D];
     double* lw;
+    double* wt;                 // exp(lw - c) against the step-wide shift c (what the resampling scan reads)
     long long n;
     AncestorMap am;
     Ctrl* ctrl;
@@ -87,7 +91,7 @@ struct StepArgs {
     const double* znoise;       // injected standard normals in the reference's consumption order, or null
     const double* ures;         // injected resampling base uniforms, one per step, or null
     long long tcap;
-    int dbg;                    // experiment switches (0 in production): 1 identity ancestors, 2 no stores, 4 no RNG, 8 no LSE
+    int dbg;                    // experiment switches (0 in production): 1 identity ancestors, 2 no stores, 4 no RNG, 32 mispredict the weight shift
     IslandInfo isl;             // island mode only
 };
 
@@ -117,6 +121,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     const int resampled = PHASE == PHASE_INIT ? 0 : a.ctrl->resampled;
     const double lse_prev = a.ctrl->lse;
     const double log_n = a.ctrl->log_n;
+    // shift of this step's stored weights (predicted by the previous step; checked against the true maximum at the end)
+    const double cbase = PHASE == PHASE_INIT ? -log_n : a.ctrl->cbase;
+    const double cs = (PHASE == PHASE_INIT ? -log_n : a.ctrl->cshift) + ((a.dbg & 32) ? 1000.0 : 0.0);
     const int parity = a.ctrl->parity;
     const unsigned long long seed = a.ctrl->seed;
     typename Model::Params prm = a.params;
@@ -133,8 +140,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     for (long long i = (long long)blockIdx.x * STEP_THREADS + tid; i < a.nstatus; i += (long long)gridDim.x * STEP_THREADS)
         a.status[i] = 0ull;
 
-    LseAcc<G> acc, acc1;   // one per particle of the pair, merged after the loop
-    acc.clear(); acc1.clear();
+    WAcc<G> acc;   // sums of the shifted weights exp(lw - cs) and the running maximum
+    acc.clear();
     double obs0 = 0.0, obs[NOBS > 0 ? NOBS : 1];
 #pragma unroll
     for (int j = 0; j < NOBS; ++j) obs[j] = 0.0;
@@ -310,9 +317,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                                         (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) + p : p), k, z[0][k], z[1][k]);
                 }
             }
-            double lwo[2] = {0.0, 0.0};
+            double lwo[2] = {0.0, 0.0}, wo[2] = {0.0, 0.0};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {   // straight-line for both particles: independent dependency chains, one accumulator each
+            for (int h = 0; h < 2; ++h) {   // straight-line for both particles: independent dependency chains
                 double lw;
                 if (PHASE == PHASE_INIT) {
                     Model::init(x[h], lw, prm, z[h]);   // moveset.h:133-138
@@ -325,33 +332,35 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 double hs[G > 0 ? G : 1];
                 Model::shift_stat(x[h], hs);
                 if (h == 1) lw = has1 ? lw : -INFINITY;   // a missing odd tail contributes nothing
-                if (h == 0) acc.add(lw, hs); else acc1.add(lw, hs);
+                wo[h] = acc.add(lw, cs, hs);               // the step's only exponential per particle
             }
             if (!(a.dbg & 2)) {
                 if (has1) {   // both particles of the pair: one 16-byte store per array (s0 is even, arrays are 256-byte aligned)
 #pragma unroll
                     for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0) = make_double2(x[0][d], x[1][d]);
                     *reinterpret_cast<double2*>(a.lw + s0) = make_double2(lwo[0], lwo[1]);
+                    *reinterpret_cast<double2*>(a.wt + s0) = make_double2(wo[0], wo[1]);
                 } else {
 #pragma unroll
                     for (int d = 0; d < D; ++d) dst[d][s0] = x[0][d];
                     a.lw[s0] = lwo[0];
+                    a.wt[s0] = wo[0];
                 }
             }
         }
     }
 
-    // ---- block reduction
-    constexpr int NF = 4 + G + NOBS;  // m, s, q, obs0, g[G], obs[NOBS]
+    // ---- block reduction: plain sums against the common shift (fixed order => reproducible) + the maximum log-weight
+    constexpr int NF = 4 + G + NOBS;  // mx, s, q, obs0, g[G], obs[NOBS]
     __shared__ double s_red[STEP_THREADS / 32][NF];
-    __shared__ bool s_last;
-    acc.merge(acc1);
+    __shared__ double s_fin[NF + 1];
+    __shared__ int s_flag;            // bit 0: this is the last block; bit 1: the predicted shift was unusable
     acc.warp_reduce();
     obs0 = warp_sum(obs0);
 #pragma unroll
     for (int j = 0; j < NOBS; ++j) obs[j] = warp_sum(obs[j]);
     if (lane == 0) {
-        s_red[warp][0] = acc.m; s_red[warp][1] = acc.s; s_red[warp][2] = acc.q; s_red[warp][3] = obs0;
+        s_red[warp][0] = acc.mx; s_red[warp][1] = acc.s; s_red[warp][2] = acc.q; s_red[warp][3] = obs0;
 #pragma unroll
         for (int j = 0; j < G; ++j) s_red[warp][4 + j] = acc.g[j];
 #pragma unroll
@@ -359,113 +368,153 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     }
     __syncthreads();
     if (tid == 0) {
-        LseAcc<G> b; b.clear();
-        double o0 = 0.0, o[NOBS > 0 ? NOBS : 1];
+        double v[NF];
 #pragma unroll
-        for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
-        for (int w = 0; w < STEP_THREADS / 32; ++w) {
-            LseAcc<G> t;
-            t.m = s_red[w][0]; t.s = s_red[w][1]; t.q = s_red[w][2];
+        for (int f = 0; f < NF; ++f) v[f] = s_red[0][f];
+        for (int w = 1; w < STEP_THREADS / 32; ++w) {
+            v[0] = fmax(v[0], s_red[w][0]);
 #pragma unroll
-            for (int j = 0; j < G; ++j) t.g[j] = s_red[w][4 + j];
-            b.merge(t);
-            o0 += s_red[w][3];
-#pragma unroll
-            for (int j = 0; j < NOBS; ++j) o[j] += s_red[w][4 + G + j];
+            for (int f = 1; f < NF; ++f) v[f] += s_red[w][f];
         }
         const int nb = gridDim.x;
-        double* P = a.partial;
-        P[0 * nb + blockIdx.x] = b.m; P[1 * nb + blockIdx.x] = b.s; P[2 * nb + blockIdx.x] = b.q; P[3 * nb + blockIdx.x] = o0;
 #pragma unroll
-        for (int j = 0; j < G; ++j) P[(4 + j) * nb + blockIdx.x] = b.g[j];
-#pragma unroll
-        for (int j = 0; j < NOBS; ++j) P[(4 + G + j) * nb + blockIdx.x] = o[j];
+        for (int f = 0; f < NF; ++f) a.partial[f * nb + blockIdx.x] = v[f];
         __threadfence();
         unsigned prev = atomicAdd(&a.ctrl->done, 1u);
-        s_last = (prev == (unsigned)nb - 1u);
+        s_flag = (prev == (unsigned)nb - 1u) ? 1 : 0;
     }
     __syncthreads();
-    if (!s_last || warp != 0) return;
+    if (!(s_flag & 1)) return;
 
-    // ---- last block, warp 0: merge the per-block partials in a fixed order and close the step
+    // ---- last block: merge the per-block partials in a fixed order and close the step
     __threadfence();
-    {
+    double cs_used = cs;
+    if (warp == 0) {
         const int nb = gridDim.x;
         const volatile double* P = a.partial;
-        LseAcc<G> b; b.clear();
-        double o0 = 0.0, o[NOBS > 0 ? NOBS : 1];
+        double v[NF];
+        v[0] = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
+        for (int f = 1; f < NF; ++f) v[f] = 0.0;
         for (int k = lane; k < nb; k += 32) {
-            LseAcc<G> t;
-            t.m = P[0 * nb + k]; t.s = P[1 * nb + k]; t.q = P[2 * nb + k];
+            v[0] = fmax(v[0], P[k]);
 #pragma unroll
-            for (int j = 0; j < G; ++j) t.g[j] = P[(4 + j) * nb + k];
-            b.merge(t);
-            o0 += P[3 * nb + k];
-#pragma unroll
-            for (int j = 0; j < NOBS; ++j) o[j] += P[(4 + G + j) * nb + k];
+            for (int f = 1; f < NF; ++f) v[f] += P[f * nb + k];
         }
-        b.warp_reduce();
-        o0 = warp_sum(o0);
+        v[0] = warp_max(v[0]);
 #pragma unroll
-        for (int j = 0; j < NOBS; ++j) o[j] = warp_sum(o[j]);
+        for (int f = 1; f < NF; ++f) v[f] = warp_sum(v[f]);
         if (ISLAND) {
             // all-gather the per-island tuples through the peer mailboxes and merge them in rank order (same bits on every rank)
-            static_assert(4 + G + NOBS <= ISL_PAYLOAD, "island message too small for this model");
+            static_assert(NF <= ISL_PAYLOAD, "island message too small for this model");
             __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
-            double mine[ISL_PAYLOAD];
-            mine[0] = b.m; mine[1] = b.s; mine[2] = b.q; mine[3] = o0;
-#pragma unroll
-            for (int j = 0; j < G; ++j) mine[4 + j] = b.g[j];
-#pragma unroll
-            for (int j = 0; j < NOBS; ++j) mine[4 + G + j] = o[j];
             const unsigned long long seq = (a.isl.epoch << 24) + (unsigned long long)(PHASE == PHASE_OBSERVE ? T : tcur) + 1ull;
-            island_allgather(a.isl, PHASE == PHASE_OBSERVE ? ISL_KIND_OBS : ISL_KIND_LSE, seq, mine, 4 + G + NOBS, s_all);
-            b.clear(); o0 = 0.0;
+            island_allgather(a.isl, PHASE == PHASE_OBSERVE ? ISL_KIND_OBS : ISL_KIND_LSE, seq, v, NF, s_all);
+            v[0] = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < NOBS; ++j) o[j] = 0.0;
+            for (int f = 1; f < NF; ++f) v[f] = 0.0;
             for (int h = 0; h < a.isl.world; ++h) {
-                LseAcc<G> t;
-                t.m = s_all[h][0]; t.s = s_all[h][1]; t.q = s_all[h][2];
+                v[0] = fmax(v[0], s_all[h][0]);
 #pragma unroll
-                for (int j = 0; j < G; ++j) t.g[j] = s_all[h][4 + j];
-                b.merge(t);
-                o0 += s_all[h][3];
-#pragma unroll
-                for (int j = 0; j < NOBS; ++j) o[j] += s_all[h][4 + G + j];
+                for (int f = 1; f < NF; ++f) v[f] += s_all[h][f];
             }
         }
         if (lane == 0) {
-            Ctrl* c = a.ctrl;
-            if (PHASE != PHASE_INIT && NOBS > 0 && T < a.tcap) {
-                double v[NOBS > 0 ? NOBS : 1], out[NOBS > 0 ? NOBS : 1];
 #pragma unroll
-                for (int j = 0; j < NOBS; ++j) v[j] = o[j] / o0;
-                Model::finish_obs(v, shift, out);
-#pragma unroll
-                for (int j = 0; j < NOBS; ++j) a.tr.obs[T * NOBS + j] = out[j];
-            }
-            if (PHASE != PHASE_OBSERVE) {
-                double lse = b.m + log(b.s);                 // stableLogSumWeights, population.h:46-50
-                double path = (PHASE == PHASE_INIT ? 0.0 : c->lognc_path) + lse;  // sampler.h:498-499, :710-711
-                double ess = (b.s * b.s) / b.q;              // sampler.h:413-417 on the normalised weights
-                int res = ess < c->thr ? 1 : 0;              // sampler.h:507, :719
-                c->lse = lse; c->lognc_path = path; c->ess = ess; c->resampled = res;
-                c->T = tcur; c->parity = parity ^ 1;
-#pragma unroll
-                for (int j = 0; j < G; ++j) c->shift[j] = b.g[j] / b.s;
-                double U;
-                if (a.ures) U = a.ures[tcur];
-                else U = u64_to_unit(philox_draw(seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
-                c->u_res = U;
-                if (tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
-            }
-            c->ticket = 0u;
-            c->ticket2 = 0u;
-            c->floor_total = 0ull;
-            c->done = 0u;
+            for (int f = 0; f < NF; ++f) s_fin[f] = v[f];
+            // usable shift: the largest shifted weight e^(M - c) and its square must stay far from overflow, and the particles
+            // that matter (within e^-37 of the maximum) far from underflow
+            const double d = v[0] - cs;
+            const bool bad = PHASE != PHASE_OBSERVE && (d <= -250.0 || d >= 250.0) && v[0] != -INFINITY;
+            s_flag = bad ? 3 : 1;
         }
+    }
+    __syncthreads();
+    if (PHASE != PHASE_OBSERVE && (s_flag & 2)) {
+        // Cold path (a weight level that jumped by more than e^250 between two steps): redo the sums against the true maximum
+        // M from the stored log-weights and rewrite the shifted weights.  One block, but only ever taken on such a jump.
+        const double M = s_fin[0];
+        WAcc<G> r; r.clear();
+        for (long long i = tid; i < n; i += STEP_THREADS) {
+            double xi[D], hs[G > 0 ? G : 1];
+#pragma unroll
+            for (int d = 0; d < D; ++d) xi[d] = dst[d][i];
+            Model::shift_stat(xi, hs);
+            a.wt[i] = r.add(a.lw[i], M, hs);
+        }
+        r.warp_reduce();
+        __syncthreads();   // s_red is being reused
+        if (lane == 0) {
+            s_red[warp][1] = r.s; s_red[warp][2] = r.q;
+#pragma unroll
+            for (int j = 0; j < G; ++j) s_red[warp][4 + j] = r.g[j];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double v[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) v[f] = 0.0;
+            for (int w = 0; w < STEP_THREADS / 32; ++w) {
+                v[1] += s_red[w][1]; v[2] += s_red[w][2];
+#pragma unroll
+                for (int j = 0; j < G; ++j) v[4 + j] += s_red[w][4 + j];
+            }
+            if (ISLAND) {
+                __shared__ double s_all2[ISL_MAX][ISL_PAYLOAD];
+                const unsigned long long seq = (a.isl.epoch << 24) + (unsigned long long)tcur + 1ull;
+                island_allgather(a.isl, ISL_KIND_LSE2, seq, v, NF, s_all2);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) v[f] = 0.0;
+                for (int h = 0; h < a.isl.world; ++h) {
+#pragma unroll
+                    for (int f = 1; f < NF; ++f) v[f] += s_all2[h][f];
+                }
+            }
+            if (lane == 0) {
+                s_fin[1] = v[1]; s_fin[2] = v[2];
+#pragma unroll
+                for (int j = 0; j < G; ++j) s_fin[4 + j] = v[4 + j];
+            }
+        }
+        __syncthreads();
+        cs_used = M;
+    }
+    if (tid == 0) {
+        Ctrl* c = a.ctrl;
+        const double mx = s_fin[0], ssum = s_fin[1], qsum = s_fin[2], o0 = s_fin[3];
+        if (PHASE != PHASE_INIT && NOBS > 0 && T < a.tcap) {
+            double v[NOBS > 0 ? NOBS : 1], out[NOBS > 0 ? NOBS : 1];
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) v[j] = s_fin[4 + G + j] / o0;
+            Model::finish_obs(v, shift, out);
+#pragma unroll
+            for (int j = 0; j < NOBS; ++j) a.tr.obs[T * NOBS + j] = out[j];
+        }
+        if (PHASE != PHASE_OBSERVE) {
+            double lse = cs_used + log(ssum);                // stableLogSumWeights, population.h:46-50
+            double path = (PHASE == PHASE_INIT ? 0.0 : c->lognc_path) + lse;  // sampler.h:498-499, :710-711
+            double ess = (ssum * ssum) / qsum;               // sampler.h:413-417 on the normalised weights
+            int res = ess < c->thr ? 1 : 0;                  // sampler.h:507, :719
+            c->lse = lse; c->lognc_path = path; c->ess = ess; c->resampled = res;
+            c->inv_s = 1.0 / ssum;
+            c->T = tcur; c->parity = parity ^ 1;
+#pragma unroll
+            for (int j = 0; j < G; ++j) c->shift[j] = s_fin[4 + j] / ssum;
+            // shift of the next step's weights: the level the log-weights start from, plus this step's largest increment
+            const double base_next = res ? -log_n : mx - lse;
+            double c_next = base_next + (mx - cbase);
+            if (!(fabs(c_next) < 1e300)) c_next = base_next;
+            c->cbase = base_next; c->cshift = c_next;
+            double U;
+            if (a.ures) U = a.ures[tcur];
+            else U = u64_to_unit(philox_draw(seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
+            c->u_res = U;
+            if (tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
+        }
+        c->ticket = 0u;
+        c->ticket2 = 0u;
+        c->floor_total = 0ull;
+        c->done = 0u;
     }
 }
 
@@ -502,6 +551,7 @@ public:
         // experiment switches for profiling sessions (0 in production), read once per sampler
         { const char* e = getenv("SMCB200_DBG_STEP"); dbg_step_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_DBG_SCAN"); dbg_scan_ = e ? atoi(e) : 0; }
+        { const char* e = getenv("SMCB200_SCAN_IMPL"); scan_impl_ = e ? atoi(e) : 1; }   // 0: block-tiled kernel (A/B measurements)
         ntiles_ = scan_tiles(n);
         surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
         // ---- slab layout (256-byte aligned sub-allocations)
@@ -510,8 +560,10 @@ public:
         size_t o_xa[D], o_xb[D];
         for (int d = 0; d < D; ++d) { o_xa[d] = take(sizeof(double) * n); o_xb[d] = take(sizeof(double) * n); }
         size_t o_lw = take(sizeof(double) * n);
+        size_t o_wt = take(sizeof(double) * n);
         size_t o_zm = take(sizeof(uint32_t) * ((n + 31) / 32 + 64)), o_zb = take(sizeof(uint32_t) * ((n + 31) / 32 + 64));
         size_t o_su = take(sizeof(uint32_t) * surplus_cap_);
+        size_t o_cs = take(sizeof(uint32_t) * resample_cslot_entries(n));
         size_t o_st = take(sizeof(unsigned long long) * 3 * ntiles_);
         size_t o_ct = take(sizeof(Ctrl));
         size_t o_t0 = take(sizeof(double) * tcap), o_t1 = take(sizeof(double) * tcap), o_t2 = take(sizeof(int) * tcap);
@@ -519,7 +571,7 @@ public:
         size_t o_mb = take(sizeof(IslMsg) * ISL_KINDS * 2 * ISL_MAX);
         grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
         grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
-        grid_scan_ = resample_scan_grid<SRC_LOGW, SYSTEMATIC>(n);
+        grid_scan_ = resample_pass_grid(n);
         int gmax = grid_init_ > grid_move_ ? grid_init_ : grid_move_;
         size_t o_pa = take(sizeof(double) * (size_t)(4 + G + NOBS) * gmax);
         size_t o_mp = take(sizeof(unsigned long long) * 1024);
@@ -533,8 +585,10 @@ public:
         SMCB_CUDA(cudaMemsetAsync(slab_ + o_mp, 0, sizeof(unsigned long long) * 1024, stream_));
         for (int d = 0; d < D; ++d) { xa_[d] = (double*)(slab_ + o_xa[d]); xb_[d] = (double*)(slab_ + o_xb[d]); }
         lw_ = (double*)(slab_ + o_lw);
+        wt_ = (double*)(slab_ + o_wt);
         am_.zmask = (uint32_t*)(slab_ + o_zm); am_.zbase = (uint32_t*)(slab_ + o_zb); am_.surplus = (uint32_t*)(slab_ + o_su);
         status_ = (unsigned long long*)(slab_ + o_st);
+        cslot_ = (uint32_t*)(slab_ + o_cs);
         ctrl_ = (Ctrl*)(slab_ + o_ct);
         tr_.lognc = (double*)(slab_ + o_t0); tr_.ess = (double*)(slab_ + o_t1); tr_.resampled = (int*)(slab_ + o_t2); tr_.obs = (double*)(slab_ + o_t3);
         partial_ = (double*)(slab_ + o_pa);
@@ -719,6 +773,7 @@ private:
     Ctrl fresh_ctrl() const {
         Ctrl h{};
         h.thr = thr_; h.log_n = std::log((double)n_glob_); h.parity = 1;  // init writes buffer A (dst of parity 1)
+        h.cshift = h.cbase = -h.log_n; h.inv_s = 1.0;
         h.seed = seed_;
         for (int k = 0; k < 4; ++k) h.mparam[k] = dyn_[k];
         return h;
@@ -740,7 +795,7 @@ private:
     StepArgs<Model> args() {
         StepArgs<Model> a;
         for (int d = 0; d < D; ++d) { a.xa[d] = xa_[d]; a.xb[d] = xb_[d]; }
-        a.lw = lw_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
+        a.lw = lw_; a.wt = wt_; a.n = n_; a.am = am_; a.ctrl = ctrl_; a.tr = tr_; a.partial = partial_;
         a.status = status_; a.nstatus = 3 * ntiles_; a.params = params_; a.seed = seed_;
         a.znoise = znoise_; a.ures = ures_; a.tcap = tcap_; a.isl = isl_;
         a.dbg = dbg_step_;
@@ -754,20 +809,24 @@ private:
         s.am = am_; s.count_out = nullptr; s.tail_info = nullptr;
         s.dbg = dbg_scan_;
         s.n_glob = n_glob_; s.surplus_cap = surplus_cap_; s.isl = isl_;
+        s.cslot = cslot_;
         if (island()) {
             if (mode_ != SYSTEMATIC && mode_ != STRATIFIED)
                 throw std::invalid_argument("island mode supports SYSTEMATIC and STRATIFIED resampling");
-            // where does this rank's cumulative weight start?  integer mass of the lower ranks (all-gathered in-kernel)
-            MassArgs m{};
-            m.lw = lw_; m.n = n_; m.lse_ptr = &ctrl_->lse; m.enable_ptr = &ctrl_->resampled; m.step_ptr = &ctrl_->T;
-            m.partial = mass_partial_ + 8; m.done = (unsigned int*)mass_partial_; m.mass_offset_out = &ctrl_->mass_offset; m.isl = isl_;
-            int g = 2 * grid_move_ < 1000 ? 2 * grid_move_ : 1000;
-            k_mass_total<<<g, 256, 0, stream_>>>(m);
-            SMCB_CUDA(cudaGetLastError());
+            // the mass pass all-gathers every rank's exact weight mass: each rank then knows where its cumulative weight starts
+            s.mass_offset_ptr = &ctrl_->mass_offset; s.mass_offset_out = &ctrl_->mass_offset;
+            s.zoff_out = ctrl_->zoff; s.eoff_out = ctrl_->eoff;
+            s.done = (unsigned int*)(mass_partial_ + 4);
+            s.in = wt_; s.lse_ptr = &ctrl_->inv_s;
+            if (mode_ == SYSTEMATIC) launch_resample_passes<SRC_WTILDE, SYSTEMATIC, true>(s, stream_);
+            else launch_resample_passes<SRC_WTILDE, STRATIFIED, true>(s, stream_);
             if (after_launch_) after_launch_();
-            s.mass_offset_ptr = &ctrl_->mass_offset; s.zoff_out = ctrl_->zoff; s.eoff_out = ctrl_->eoff;
-            if (mode_ == SYSTEMATIC) launch_resample_scan<SRC_LOGW, SYSTEMATIC, true>(s, stream_);
-            else launch_resample_scan<SRC_LOGW, STRATIFIED, true>(s, stream_);
+            return;
+        }
+        if (scan_impl_ == 1 && (mode_ == SYSTEMATIC || mode_ == STRATIFIED)) {
+            s.in = wt_; s.lse_ptr = &ctrl_->inv_s;   // shifted weights x 1/sum: no exponential in the resampling passes
+            if (mode_ == SYSTEMATIC) launch_resample_passes<SRC_WTILDE, SYSTEMATIC>(s, stream_);
+            else launch_resample_passes<SRC_WTILDE, STRATIFIED>(s, stream_);
             if (after_launch_) after_launch_();
             return;
         }
@@ -790,7 +849,7 @@ private:
 
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
-    int dbg_step_ = 0, dbg_scan_ = 0;
+    int dbg_step_ = 0, dbg_scan_ = 0, scan_impl_ = 1;
     double dyn_[4] = {0.0, 0.0, 0.0, 0.0};
     cudaGraphExec_t graph_exec_ = nullptr;
     cudaStream_t graph_stream_ = nullptr;
@@ -810,8 +869,10 @@ private:
     double* xa_[D];
     double* xb_[D];
     double* lw_ = nullptr;
+    double* wt_ = nullptr;
     AncestorMap am_{};
     unsigned long long* status_ = nullptr;
+    uint32_t* cslot_ = nullptr;
     Ctrl* ctrl_ = nullptr;
     Traces tr_{};
     double* partial_ = nullptr;

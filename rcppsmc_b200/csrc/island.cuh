@@ -11,7 +11,7 @@ namespace smcb {
 
 constexpr int ISL_MAX = 8;        // ranks on one NVSwitch box
 constexpr int ISL_PAYLOAD = 16;   // doubles per message
-enum { ISL_KIND_LSE = 0, ISL_KIND_MASS = 1, ISL_KIND_ZE = 2, ISL_KIND_OBS = 3, ISL_KINDS = 4 };
+enum { ISL_KIND_LSE = 0, ISL_KIND_MASS = 1, ISL_KIND_ZE = 2, ISL_KIND_OBS = 3, ISL_KIND_LSE2 = 4, ISL_KINDS = 5 };
 
 struct IslMsg {                   // one mailbox slot (written by exactly one peer)
     unsigned long long seq;       // written last; the reader spins on it

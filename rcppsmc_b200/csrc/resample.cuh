@@ -12,6 +12,8 @@
 //   * replication (:860-864)                         -> NOT done here: the ancestor of slot s is decoded in
 //     the next propagate kernel's gather from (zmask, zbase, surplus): 2 bits + 4 B per zero-count slot.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 #include "philox.cuh"
 #include "island.cuh"
@@ -224,6 +226,9 @@ struct ScanArgs {
     const unsigned long long* mass_offset_ptr;
     long long* zoff_out;      // [world+1] written by the last tile after the all-gather of (zero slots, surplus entries)
     long long* eoff_out;
+    unsigned int* done;       // island mode: blocks-finished counter (zero on entry, reset by the kernels)
+    unsigned long long* mass_offset_out;   // island mode: written by the mass pass (mass of the lower ranks)
+    uint32_t* cslot;          // three-pass path: children handed out up to each slot, resample_cslot_entries(n) entries
     IslandInfo isl;
 };
 
@@ -327,7 +332,9 @@ __device__ __forceinline__ void finish_heavy_runs(uint32_t* __restrict__ surplus
     }
 }
 
-inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+// Entries per look-back status array: sized for the smallest tile any resampling kernel uses (the warp tile, 256 slots) plus
+// two words per group of 32 such tiles (second level of the warp kernel's look-back).
+inline long long scan_tiles(long long n) { return (n + 255) / 256 + 2 * ((n + 8191) / 8192) + 2; }
 
 // One pass: weights -> (zmask, zbase, surplus).  Persistent blocks pull 1024-slot tiles from a ticket counter and keep
 // FOUR tiles in flight, one per pipeline stage, so that neither look-back chain is ever waited on right after its
@@ -626,11 +633,410 @@ inline void launch_resample_scan(const ScanArgs& a, cudaStream_t stream) {
     SMCB_CUDA(cudaGetLastError());
 }
 
+// =====================================================================================================================
+// Three-pass resampling without any waiting between thread blocks (the production path for SYSTEMATIC / STRATIFIED).
+//
+// Same mathematics and the same outputs as the single-pass kernel above; the two prefix dependencies (weight mass, zero-count
+// slots) are resolved at kernel boundaries instead of by look-back chains:
+//   k_rs_mass   tile masses   (256-slot warp tiles; every tile's exact mass + atomically accumulated masses of 128-tile "supers")
+//   k_rs_count  mass prefix of the tile from (supers, tiles) -> exact cumulative weights -> children handed out up to each slot
+//               (stored, 4 B per slot) -> zero-slot bitmap, zero-slot totals per tile / super
+//   k_rs_map    zero-slot prefix from (supers, tiles) -> rank bases + surplus lists
+// A warp owns whole tiles (blocked: lane l holds 8 consecutive slots in registers), all scans are register + shuffle scans,
+// there is no shared memory and no __syncthreads.  Every pass streams at HBM speed; nothing ever spins on another block, so
+// the passes are indifferent to what else runs on the GPU.  Measured alternatives (profiles/r2_scan_experiments.txt): the
+// block-tiled single pass above (177 us per 2^24 slots: barrier + look-back latency bound) and a warp-granular single pass
+// with one- and two-level look-back chains (340 - 960 us: every tile couples to the slowest of its ~64 predecessors).
+constexpr int RP_ITEMS = 8;
+constexpr int RP_TILE = 32 * RP_ITEMS;          // slots per warp tile
+constexpr int RP_SUPER = 128;                   // tiles per super
+constexpr int RP_THREADS = 256;
+static_assert(RP_TILE == 256, "scan_tiles() sizes the per-tile arrays for 256-slot tiles");
+
+enum { SRC_WTILDE = 2 };   // weights exp(lw - c) against a step-wide shift c, normalised by one multiplication (k_step writes them)
+
+struct RsView {            // how the three passes see the workspace of ScanArgs
+    double* tile_mass;                 // [ntiles]  exact mass of each tile (multiple of 2^-52)
+    unsigned long long* tile_z;        // [ntiles]  zero-count slots of each tile
+    unsigned long long* super_mass;    // [nsuper]  fixed-point (2^-52) mass of each super, accumulated atomically (zero on entry)
+    unsigned long long* super_z;       // [nsuper]  zero-count slots of each super (zero on entry)
+};
+__device__ __forceinline__ RsView rs_view(const ScanArgs& a, int ntiles) {
+    RsView v;
+    v.tile_mass = reinterpret_cast<double*>(a.ws.statusA);
+    v.tile_z = a.ws.statusB;
+    v.super_mass = a.ws.statusC;
+    v.super_z = a.ws.statusC + (ntiles + RP_SUPER - 1) / RP_SUPER;
+    return v;
+}
+template <int SRC>
+__device__ __forceinline__ double rs_quantise(double raw, double lse, double inv_s) {
+    const double w = (SRC == SRC_LOGW) ? fm_exp(raw - lse) : (SRC == SRC_WTILDE ? raw * inv_s : raw);
+    return (w + 1.0) - 1.0;                     // round to the 2^-52 grid (ulp of [1,2)); all sums of such values below 2 are exact
+}
+// contiguous chunk of tiles owned by a warp: [t0, t1)
+__device__ __forceinline__ void rs_chunk(int ntiles, int& t0, int& t1) {
+    const int nw = (int)(gridDim.x * (RP_THREADS / 32));
+    const int w = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5));
+    const int per = (ntiles + nw - 1) / nw;
+    t0 = min(w * per, ntiles);
+    t1 = min(t0 + per, ntiles);
+}
+
+template <int SRC, bool ISLAND>
+__global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int n32 = (int)a.n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const RsView V = rs_view(a, ntiles);
+    const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
+    const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;   // SRC_WTILDE: lse_ptr points at 1 / sum of the shifted weights
+    const int nw = (int)(gridDim.x * (RP_THREADS / 32));
+    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
+        const int base = tile * RP_TILE;
+        double s = 0.0;
+        if (base + RP_TILE <= n32) {   // coalesced 16-byte loads; the order inside a tile does not matter for an exact sum
+            const double2* p = reinterpret_cast<const double2*>(a.in + base) + lane;
+            double2 v[RP_ITEMS / 2];
+#pragma unroll
+            for (int r = 0; r < RP_ITEMS / 2; ++r) v[r] = p[32 * r];
+#pragma unroll
+            for (int r = 0; r < RP_ITEMS / 2; ++r) s += rs_quantise<SRC>(v[r].x, lse, inv_s) + rs_quantise<SRC>(v[r].y, lse, inv_s);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RP_ITEMS; ++r) {
+                const int i = base + r * 32 + lane;
+                if (i < n32) s += rs_quantise<SRC>(a.in[i], lse, inv_s);
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            V.tile_mass[tile] = s;
+            atomicAdd(V.super_mass + tile / RP_SUPER, (unsigned long long)__double2ll_rn(s * TWO52));
+        }
+    }
+    if (ISLAND) {
+        // this rank's total mass -> all-gather -> where does this rank's cumulative weight start (mass of the lower ranks)
+        __shared__ bool s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u; }
+        __syncthreads();
+        if (!s_last || threadIdx.x >= 32) return;
+        __threadfence();
+        const int nsuper = (ntiles + RP_SUPER - 1) / RP_SUPER;
+        unsigned long long tot = 0ull;
+        for (int k = lane; k < nsuper; k += 32) tot += reinterpret_cast<volatile unsigned long long*>(V.super_mass)[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(SMCB_FULL, tot, o);
+        __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
+        double mine[1] = {(double)tot};   // < 2^53: exact
+        island_allgather(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)(*a.step_ptr) + 1ull, mine, 1, s_all);
+        if (lane == 0) {
+            unsigned long long off = 0ull;
+            for (int h = 0; h < a.isl.rank; ++h) off += (unsigned long long)s_all[h][0];
+            *a.mass_offset_out = off;
+            *a.done = 0u;
+        }
+    }
+}
+
+template <int SRC, int MODE, bool ISLAND, bool POW2>
+__device__ __forceinline__ void rs_count_body(const ScanArgs& a) {
+    const int lane = threadIdx.x & 31;
+    const long long n = a.n;
+    const int n32 = (int)n;
+    const long long nthr = ISLAND ? a.n_glob : n;          // N of the resampling thresholds j/N
+    const double nd = (double)nthr;
+    const double inv_n = 1.0 / nd;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const RsView V = rs_view(a, ntiles);
+    const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
+    const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;
+    const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
+    const long long step = a.step_ptr ? *a.step_ptr : 0;
+    const double mass0 = ISLAND ? u64_to_double_exact(*a.mass_offset_ptr) * INV_TWO52 : 0.0;   // weight mass of lower ranks
+    const int cstart = ISLAND ? children_upto<MODE, POW2>(mass0, a, nthr, nd, inv_n, dRand, step) : 0;
+    int t0, t1;
+    rs_chunk(ntiles, t0, t1);
+    if (t0 >= t1) return;
+    // exact mass in front of the chunk: whole supers, then the tiles of the super the chunk starts in
+    double P;
+    {
+        const int s0 = t0 / RP_SUPER;
+        double acc = 0.0;
+        for (int k = lane; k < s0; k += 32) acc += u64_to_double_exact(V.super_mass[k]) * INV_TWO52;
+        for (int k = s0 * RP_SUPER + lane; k < t0; k += 32) acc += V.tile_mass[k];
+        P = warp_sum(acc) + mass0;
+    }
+    // blocked load of a tile: lane l reads 8 consecutive doubles (16-byte vectors; slabs and tiles are 256-byte aligned)
+    auto load_tile = [&](int t, double (&r)[RP_ITEMS]) {
+        const int g = t * RP_TILE + lane * RP_ITEMS;
+        if (g + RP_ITEMS <= n32) {
+            const double2* p = reinterpret_cast<const double2*>(a.in + g);
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS / 2; ++k) { const double2 v = p[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) r[k] = g + k < n32 ? a.in[g + k] : 0.0;
+        }
+    };
+    double raw[RP_ITEMS];
+    load_tile(t0, raw);
+    for (int tile = t0; tile < t1; ++tile) {
+        const int g0 = tile * RP_TILE + lane * RP_ITEMS;       // local slot id of the lane's first slot (n < 2^31)
+        const int nv = min(max(n32 - g0, 0), RP_ITEMS);         // valid slots of this lane
+        double cum[RP_ITEMS];
+        {
+            double run = 0.0;
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) {
+                double q = rs_quantise<SRC>(raw[k], lse, inv_s);
+                if (k >= nv) q = 0.0;
+                run += q;
+                cum[k] = run;
+            }
+        }
+        if (tile + 1 < t1) load_tile(tile + 1, raw);            // the next tile's input is in flight during the arithmetic below
+        const double tot = cum[RP_ITEMS - 1];
+        double inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(SMCB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const double lane_excl = P + (inc - tot);               // exact
+        P += __shfl_sync(SMCB_FULL, inc, 31);
+        // children handed out up to each slot (closed form with the reference's predicate), relative to this rank's start
+        int cprev = children_upto<MODE, POW2>(lane_excl, a, nthr, nd, inv_n, dRand, step) - cstart;
+        uint32_t c[RP_ITEMS];
+        unsigned zbits = 0u;
+#pragma unroll
+        for (int k = 0; k < RP_ITEMS; ++k) {
+            const int ck = children_upto<MODE, POW2>(lane_excl + cum[k], a, nthr, nd, inv_n, dRand, step) - cstart;
+            if (ck == cprev) zbits |= 1u << k;
+            c[k] = (uint32_t)ck;
+            cprev = ck;
+        }
+        zbits &= (1u << nv) - 1u;
+        // c is padded to whole tiles, so the stores need no guard
+        uint4* cp = reinterpret_cast<uint4*>(a.cslot + g0);
+        cp[0] = make_uint4(c[0], c[1], c[2], c[3]);
+        cp[1] = make_uint4(c[4], c[5], c[6], c[7]);
+        {   // zero-slot bitmap: 4 lanes x 8 slots = one 32-bit word
+            unsigned m = zbits << (8 * (lane & 3));
+            m |= __shfl_xor_sync(SMCB_FULL, m, 1);
+            m |= __shfl_xor_sync(SMCB_FULL, m, 2);
+            if ((lane & 3) == 0 && g0 < n32) a.am.zmask[g0 >> 5] = m;
+        }
+        int z = __popc(zbits);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(SMCB_FULL, z, o);
+        if (lane == 0) {
+            V.tile_z[tile] = (unsigned long long)z;
+            atomicAdd(V.super_z + tile / RP_SUPER, (unsigned long long)z);
+        }
+    }
+}
+
+#ifndef SMCB_RS_COUNT_MINB
+#define SMCB_RS_COUNT_MINB 3
+#endif
+template <int SRC, int MODE, bool ISLAND>
+__global__ void __launch_bounds__(RP_THREADS, SMCB_RS_COUNT_MINB) k_rs_count(ScanArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const long long nthr = ISLAND ? a.n_glob : a.n;
+    if ((nthr & (nthr - 1)) == 0) rs_count_body<SRC, MODE, ISLAND, true>(a);
+    else rs_count_body<SRC, MODE, ISLAND, false>(a);
+}
+
+constexpr int RP_WINDOW = 512;                  // surplus entries expanded per shared-memory window (per warp)
+template <bool ISLAND>
+__global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    __shared__ uint32_t s_seg[RP_THREADS / 32][RP_WINDOW];
+    const int lane = threadIdx.x & 31;
+    const long long n = a.n;
+    const int n32 = (int)n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const RsView V = rs_view(a, ntiles);
+    const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
+    const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
+    const long long step = a.step_ptr ? *a.step_ptr : 0;
+    int t0, t1;
+    rs_chunk(ntiles, t0, t1);
+    if (t0 < t1) {
+        // zero-count slots in front of the chunk, and the children handed out before its first slot
+        int Z;
+        {
+            const int s0 = t0 / RP_SUPER;
+            unsigned long long acc = 0ull;
+            for (int k = lane; k < s0; k += 32) acc += V.super_z[k];
+            for (int k = s0 * RP_SUPER + lane; k < t0; k += 32) acc += V.tile_z[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCB_FULL, acc, o);
+            Z = (int)acc;
+        }
+        int clast = t0 > 0 ? (int)a.cslot[t0 * RP_TILE - 1] : 0;    // c of the slot in front of the tile
+        for (int tile = t0; tile < t1; ++tile) {
+            const int g0 = tile * RP_TILE + lane * RP_ITEMS;
+            const int nv = min(max(n32 - g0, 0), RP_ITEMS);
+            int c[RP_ITEMS];
+            {
+                const uint4* cp = reinterpret_cast<const uint4*>(a.cslot + g0);
+                const uint4 u = cp[0], v = cp[1];
+                c[0] = (int)u.x; c[1] = (int)u.y; c[2] = (int)u.z; c[3] = (int)u.w;
+                c[4] = (int)v.x; c[5] = (int)v.y; c[6] = (int)v.z; c[7] = (int)v.w;
+            }
+            int cfirst = __shfl_up_sync(SMCB_FULL, c[RP_ITEMS - 1], 1);
+            if (lane == 0) cfirst = clast;
+            clast = __shfl_sync(SMCB_FULL, c[RP_ITEMS - 1], 31);
+            int cnt[RP_ITEMS];
+            unsigned zbits = 0u;
+            {
+                int cp = cfirst;
+#pragma unroll
+                for (int k = 0; k < RP_ITEMS; ++k) {
+                    cnt[k] = c[k] - cp;
+                    if (cnt[k] == 0) zbits |= 1u << k;
+                    cp = c[k];
+                }
+            }
+            zbits &= (1u << nv) - 1u;
+            const int ztot = __popc(zbits);
+            int zinc = ztot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(SMCB_FULL, zinc, o);
+                if (lane >= o) zinc += t;
+            }
+            const int zexcl = Z + zinc - ztot;
+            const int zagg = __shfl_sync(SMCB_FULL, zinc, 31);
+            if ((lane & 3) == 0 && g0 < n32) a.am.zbase[g0 >> 5] = (uint32_t)zexcl;
+            {   // Surplus lists.  Parent k with count >= 2 owns surplus[E[k] .. E[k] + count - 2], E[k] = c(k-1) - k + Z[k]: the
+                // tile's entries are ONE contiguous segment in which every parent's id is repeated count-1 times, in slot
+                // order.  The warp expands it cooperatively: each parent drops a marker at the start of its run in a
+                // shared-memory window, an inclusive max-scan over the window fills the runs (ids increase along the
+                // segment), and the window is written out with coalesced stores.  Cost per entry is the same for a run of
+                // 1 and a run of 10^6: skewed weights (the reason a filter resamples) do not slow the pass down.
+                int o[RP_ITEMS];                     // start of each slot's run, relative to the tile's segment
+                int run = 0;
+#pragma unroll
+                for (int k = 0; k < RP_ITEMS; ++k) { o[k] = run; run += max(cnt[k] - 1, 0); }
+                int einc = run;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(SMCB_FULL, einc, d);
+                    if (lane >= d) einc += t;
+                }
+                const int lane_off = einc - run;
+                const int etile = __shfl_sync(SMCB_FULL, einc, 31);          // entries of this tile
+                const long long Etile = __shfl_sync(SMCB_FULL, cfirst - g0 + zexcl, 0);   // E of the tile's first slot (lanes past the end of the array have no valid E of their own)
+                uint32_t* seg = s_seg[threadIdx.x >> 5];
+                const uint32_t id0 = gslot0 + (uint32_t)(tile * RP_TILE);     // global id of the tile's first slot
+                uint32_t carry = 0u;                                         // marker (local slot + 1) in force at the window start
+                for (int w0 = 0; w0 < etile; w0 += RP_WINDOW) {
+                    const int wlen = min(etile - w0, RP_WINDOW);
+                    for (int j = lane; j < wlen; j += 32) seg[j] = 0u;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < RP_ITEMS; ++k) {
+                        const int pos = lane_off + o[k] - w0;
+                        if (cnt[k] > 1 && pos >= 0 && pos < wlen) seg[pos] = (uint32_t)(lane * RP_ITEMS + k + 1);
+                    }
+                    __syncwarp();
+                    for (int j0 = 0; j0 < wlen; j0 += 32) {
+                        const int j = j0 + lane;
+                        uint32_t v = j < wlen ? seg[j] : 0u;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(SMCB_FULL, v, d);
+                            if (lane >= d) v = max(v, t);
+                        }
+                        v = max(v, carry);
+                        carry = __shfl_sync(SMCB_FULL, v, 31);
+                        const long long m = Etile + w0 + j;
+                        if (j < wlen && m < scap) a.am.surplus[m] = id0 + v - 1u;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (a.count_out) {
+#pragma unroll
+                for (int k = 0; k < RP_ITEMS; ++k) if (k < nv) a.count_out[g0 + k] = cnt[k];
+            }
+            if (tile == ntiles - 1) {
+                // totals of this rank: children handed out, zero-count slots, surplus-list entries
+                const long long ctot = clast;
+                const long long ztotal = (long long)Z + zagg;
+                const long long etot = ctot - n + ztotal;
+                if (!ISLAND) {
+                    // unfilled zero-count slots copy particle 0 (reference: uRSIndices zero-initialised, sampler.h:845)
+                    for (long long m = etot + lane; m < ztotal; m += 32) a.am.surplus[m] = 0u;
+                    if (lane == 0 && a.tail_info) { a.tail_info[0] = (unsigned)ctot; a.tail_info[1] = (unsigned)ztotal; }
+                } else if (lane == 0) {
+                    a.zoff_out[ISL_MAX + 1] = ztotal;           // stash for the block that finishes last (below)
+                    a.eoff_out[ISL_MAX + 1] = etot;
+                }
+            }
+            Z += zagg;
+        }
+    }
+    if (ISLAND) {
+        // The all-gather of (zero slots, surplus entries) tells every rank's next gather where the m-th zero-count slot of the
+        // GLOBAL order finds its parent -- and it is the signal that this rank's surplus list may be read over NVLink.  It is
+        // therefore sent by the block that FINISHES last, after every block's surplus stores have been fenced at system scope.
+        __shared__ bool s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (!s_last || threadIdx.x >= 32) return;
+        __threadfence_system();
+        __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
+        double mine[2] = {(double)*(volatile long long*)&a.zoff_out[ISL_MAX + 1], (double)*(volatile long long*)&a.eoff_out[ISL_MAX + 1]};
+        island_allgather(a.isl, ISL_KIND_ZE, (a.isl.epoch << 24) + (unsigned long long)step + 1ull, mine, 2, s_all);
+        if (lane == 0) {
+            long long z = 0, e = 0;
+            for (int h = 0; h < a.isl.world; ++h) {
+                a.zoff_out[h] = z; a.eoff_out[h] = e;
+                z += (long long)s_all[h][0]; e += (long long)s_all[h][1];
+            }
+            a.zoff_out[a.isl.world] = z; a.eoff_out[a.isl.world] = e;
+            *a.done = 0u;
+        }
+    }
+}
+
+// Host side: one grid for the three passes (all SMs x resident blocks of the widest kernel, capped by the work available).
+inline int resample_pass_grid(long long n, int blocks_per_sm = 3) {
+    int dev = 0, sms = 0;
+    SMCB_CUDA(cudaGetDevice(&dev));
+    SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long warps_per_block = RP_THREADS / 32;
+    long long need = ((n + RP_TILE - 1) / RP_TILE + warps_per_block - 1) / warps_per_block, g = (long long)sms * blocks_per_sm;
+    if (g > need) g = need;
+    return (int)(g < 1 ? 1 : g);
+}
+// Entries of ScanArgs::cslot (children handed out up to each slot), padded to whole tiles.
+inline size_t resample_cslot_entries(long long n) { return (size_t)((n + RP_TILE - 1) / RP_TILE) * RP_TILE; }
+
+template <int SRC, int MODE, bool ISLAND = false>
+inline void launch_resample_passes(const ScanArgs& a, cudaStream_t stream, const std::function<void()>* after = nullptr) {
+    const int grid = resample_pass_grid(a.n);
+    k_rs_mass<SRC, ISLAND><<<resample_pass_grid(a.n, 8), RP_THREADS, 0, stream>>>(a);   // pure streaming: more warps in flight
+    if (after && *after) (*after)();
+    k_rs_count<SRC, MODE, ISLAND><<<grid, RP_THREADS, 0, stream>>>(a);
+    if (after && *after) (*after)();
+    k_rs_map<ISLAND><<<grid, RP_THREADS, 0, stream>>>(a);
+    SMCB_CUDA(cudaGetLastError());
+}
+
 // ---- island mode: integer weight mass of this rank, all-gathered so that every rank knows where its scan starts --------
 struct MassArgs {
-    const double* lw;
+    const double* wt;                    // shifted weights exp(lw - c) written by k_step
     long long n;
-    const double* lse_ptr;
+    const double* inv_s_ptr;             // 1 / their sum over the whole population
     const int* enable_ptr;
     const long long* step_ptr;
     unsigned long long* partial;         // [gridDim.x]
@@ -641,18 +1047,18 @@ struct MassArgs {
 
 static __global__ void __launch_bounds__(256) k_mass_total(MassArgs a) {
     if (a.enable_ptr && *a.enable_ptr == 0) return;
-    const double lse = *a.lse_ptr;
+    const double inv_s = *a.inv_s_ptr;
     // Same grid arithmetic as the scan: q = (w + 1) - 1 is w rounded to a multiple of 2^-52, and sums of such values below 2
     // are exact in fp64 in any order.  Four independent slots per thread and iteration (two 16-byte loads).
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const long long nq = a.n >> 2;
-    const double2* lw2 = reinterpret_cast<const double2*>(a.lw);
+    const double2* w2 = reinterpret_cast<const double2*>(a.wt);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nq; i += (long long)gridDim.x * 256) {
-        const double2 u = lw2[2 * i], v = lw2[2 * i + 1];
-        s0 += (fm_exp(u.x - lse) + 1.0) - 1.0; s1 += (fm_exp(u.y - lse) + 1.0) - 1.0;
-        s2 += (fm_exp(v.x - lse) + 1.0) - 1.0; s3 += (fm_exp(v.y - lse) + 1.0) - 1.0;
+        const double2 u = w2[2 * i], v = w2[2 * i + 1];
+        s0 += (u.x * inv_s + 1.0) - 1.0; s1 += (u.y * inv_s + 1.0) - 1.0;
+        s2 += (v.x * inv_s + 1.0) - 1.0; s3 += (v.y * inv_s + 1.0) - 1.0;
     }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(a.n & 3)) s0 += (fm_exp(a.lw[(nq << 2) + threadIdx.x] - lse) + 1.0) - 1.0;
+    if (blockIdx.x == 0 && threadIdx.x < (int)(a.n & 3)) s0 += (a.wt[(nq << 2) + threadIdx.x] * inv_s + 1.0) - 1.0;
     // every lane total is a multiple of 2^-52 below 2 (the weights sum to 1): the conversions are exact
     unsigned long long sum = (unsigned long long)__double2ll_rn(s0 * TWO52) + (unsigned long long)__double2ll_rn(s1 * TWO52) +
                              (unsigned long long)__double2ll_rn(s2 * TWO52) + (unsigned long long)__double2ll_rn(s3 * TWO52);

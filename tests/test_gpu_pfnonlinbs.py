@@ -141,3 +141,25 @@ def test_repeated_runs_on_one_handle_are_bit_identical(smc, mode):
         else:
             assert np.array_equal(out["logNC"], first[0]) and np.array_equal(idx, first[1])
     f.close()
+
+
+@pytest.mark.parametrize("thr", [1.01, 0.5])
+def test_mispredicted_weight_shift_takes_the_cold_path_and_still_matches(smc, monkeypatch, thr):
+    # k_step stores exp(lw - c) against a shift c predicted by the previous step; an unusable c (here: off by e^1000 through
+    # the experiment switch, so that every shifted weight underflows) must be detected and repaired from the stored log-weights
+    N, T = 5000, 12
+    y, z, U = _inject_case(N, T, H.SYSTEMATIC, seed=21)
+    monkeypatch.setenv("SMCB200_DBG_STEP", "32")
+    f = smc.PfNonlinBS(N, T, seed=1)     # the switch is read when the sampler is built
+    monkeypatch.delenv("SMCB200_DBG_STEP")
+    f.set_data(y)
+    f.set_noise(z, U)
+    f.run(H.SYSTEMATIC, thr * N if thr > 1 else thr)
+    got = f.read()
+    f.close()
+    exp = H.o_pfnonlinbs(y, N, H.SYSTEMATIC, thr * N if thr > 1 else thr, z=z, U=U, by_step=True)
+    assert np.array_equal(got["resampled"], exp["resampled"])
+    np.testing.assert_allclose(got["logNC"], exp["logNC"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(got["ESS"], exp["ESS"], rtol=RTOL)
+    np.testing.assert_allclose(got["mean"], exp["mean"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(got["sd"], exp["sd"], rtol=RTOL, atol=1e-9)
