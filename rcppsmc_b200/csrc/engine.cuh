@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdlib>
 #include <functional>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -29,12 +30,18 @@ constexpr int MAX_SHIFT = 4;
 #define SMCB_MASK_LOAD 0
 #endif
 #ifndef SMCB_STEP_MINB
-#define SMCB_STEP_MINB 2
+#define SMCB_STEP_MINB 3
 #endif
 #ifndef SMCB_STEP_THREADS
-#define SMCB_STEP_THREADS 256
+#define SMCB_STEP_THREADS 128
 #endif
 constexpr int STEP_THREADS = SMCB_STEP_THREADS;
+// Slots a thread of k_step owns per iteration: four for small states (four independent dependency chains hide the fp64
+// latency; the four slots share one bitmap word of the ancestor map), two when the state is wide (registers).
+#ifndef SMCB_STEP_Q
+#define SMCB_STEP_Q 4
+#endif
+template <class Model> struct StepShape { static constexpr int Q = Model::D <= 2 ? SMCB_STEP_Q : 2; };
 
 // Device control block: every per-step scalar of the reference sampler lives here so that a whole filter
 // runs without host round trips.  Field meanings follow sampler.h:88-128.
@@ -91,7 +98,7 @@ struct StepArgs {
     const double* znoise;       // injected standard normals in the reference's consumption order, or null
     const double* ures;         // injected resampling base uniforms, one per step, or null
     long long tcap;
-    int dbg;                    // experiment switches (0 in production): 1 identity ancestors, 2 no stores, 4 no RNG, 32 mispredict the weight shift
+    int dbg;                    // test switch (0 in production): 32 = mispredict the weight shift (exercises the cold path)
     IslandInfo isl;             // island mode only
 };
 
@@ -108,6 +115,7 @@ __device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_youngest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <class Model, int PHASE, bool INJECT, bool ISLAND = false>
 __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
@@ -146,14 +154,17 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
 #pragma unroll
     for (int j = 0; j < NOBS; ++j) obs[j] = 0.0;
 
-    // ---- particle loop, software-pipelined: the ancestor decode is a chain of three dependent loads
-    // (bitmap word -> surplus entry -> parent state), so each link is issued one iteration ahead of its use:
-    //   stage A (pair p+3S)  bitmap word + rank base          stage B (pair p+2S)  rank -> surplus loads
-    //   stage C (pair p+S)   parent state (and stored log-weight when the last step did not resample)
-    //   compute (pair p)     moments, RNG, model functor, stores, online log-sum-exp
-    // 32-bit pair / slot indices inside the loop (n < 2^31): half the integer work of 64-bit index arithmetic
+    // ---- particle loop.  A thread owns Q consecutive slots per iteration (Q = 4 for small states: four independent dependency
+    // chains per thread hide the fp64 latency, one Philox call + one Box-Muller per two slots, and the four slots share one
+    // bitmap word of the ancestor map).  The ancestor decode is a chain of three dependent loads (bitmap word -> surplus entry
+    // -> parent state), so each link is issued one iteration ahead of its use:
+    //   stage A (group p+4S)  bitmap word + rank base          stage B (group p+3S)  rank -> surplus loads
+    //   stage C (group p+2S)  parent state (and stored log-weight when the last step did not resample)
+    //   compute (group p)     moments, RNG, model functor, stores, weight sums
+    // 32-bit group / slot indices inside the loop (n < 2^31): half the integer work of 64-bit index arithmetic
+    constexpr int Q = StepShape<Model>::Q;
     const uint32_t n32 = (uint32_t)n;
-    const uint32_t npairs = (uint32_t)((n + 1) >> 1);
+    const uint32_t ngroups = (uint32_t)((n + Q - 1) / Q);
     const uint32_t stride = gridDim.x * STEP_THREADS;
     const uint32_t p0 = blockIdx.x * STEP_THREADS + tid;
     // Every link lands in shared memory through cp.async (each thread owns one slot per array and is the only reader of it, so
@@ -162,47 +173,57 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     // copy may be a peer's slab (surplus entry or parent state on another island): same instruction, NVLink underneath.
     constexpr bool ASYNC = PHASE != PHASE_INIT;
     __shared__ uint32_t s_mk[2][ASYNC ? STEP_THREADS : 1];      // bitmap word, rank base
-    __shared__ uint32_t s_sp[2][ASYNC ? STEP_THREADS : 1];      // surplus entries of the pair
-    __shared__ double s_x[2][D][ASYNC ? STEP_THREADS : 1];      // parents' state
-    __shared__ double s_lw[2][ASYNC ? STEP_THREADS : 1];        // stored log-weights (no resampling last step)
-    const bool decode = PHASE != PHASE_INIT && resampled && !(a.dbg & 1);
+    __shared__ uint32_t s_sp[Q][ASYNC ? STEP_THREADS : 1];      // surplus entries of the group
+    __shared__ double s_x[2][Q][D][ASYNC ? STEP_THREADS : 1];   // parents' state, double-buffered (gathered two iterations ahead)
+    __shared__ double s_lw[2][Q][ASYNC ? STEP_THREADS : 1];     // stored log-weights (no resampling last step), likewise
+    // The loop exists in two versions, selected by one uniform branch: after a resampling step (ancestor decode, uniform
+    // weights) and after a step that kept its population (own slot, stored log-weights).  Inside each, the last, ragged
+    // group of a population whose size is not a multiple of Q runs through a second copy of the body (FULL = false), so
+    // that the hot copy carries no per-slot existence tests.
+    auto run = [&](auto res_tag) {
+    constexpr bool RES = decltype(res_tag)::value;
+    constexpr bool decode = PHASE != PHASE_INIT && RES;
     // the thread's slots: array k of a family sits k * stride bytes after the first one
     const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][ASYNC ? tid : 0]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][ASYNC ? tid : 0]);
-    const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][ASYNC ? tid : 0]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][ASYNC ? tid : 0]);
+    const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][0][ASYNC ? tid : 0]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][0][ASYNC ? tid : 0]);
     constexpr unsigned ST4 = STEP_THREADS * 4u, ST8 = STEP_THREADS * 8u;
+    constexpr unsigned XBUF = (unsigned)(Q * D) * ST8, LBUF = (unsigned)Q * ST8;   // bytes between the two buffers
     // island mode: this rank's window of the global zero-slot ranking / surplus list / slot numbering (uniform over the kernel)
     const long long zoff_mine = (ISLAND && decode) ? a.ctrl->zoff[a.isl.rank] : 0, eoff_mine = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank] : 0;
     const long long eoff_next = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank + 1] : 0, eoff_all = (ISLAND && decode) ? a.ctrl->eoff[a.isl.world] : 0;
     const uint32_t slot_lo = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;
-    uint32_t zfB = 0u, selfB = 0u;             // stage B result: bit h = slot h takes its surplus entry, bit 2+h = slot h takes particle 0
-    double xC[2][D], lwC[2] = {0.0, 0.0};      // stage C result, read back from shared memory
+    uint32_t zfB = 0u, selfB = 0u;   // stage B result: bit h = slot h takes its surplus entry, bit 8+h = slot h takes particle 0
+    // The look-ahead of the last iterations runs past the end of the population; it is clamped to the last group instead of
+    // being branched around (the redundant copies are harmless), so that the loop body stays one basic block in which the
+    // compiler can interleave the arithmetic of the thread's Q particles.
+    const uint32_t glast = ngroups - 1u;
     auto stageA = [&](uint32_t p) {
-        if (ASYNC && decode && p < npairs) {
-            cp_async4(sa_mk, a.am.zmask + (p >> 4));
-            cp_async4(sa_mk + ST4, a.am.zbase + (p >> 4));
+        if (ASYNC && decode) {
+            const uint32_t w = (min(p, glast) * Q) >> 5;
+            cp_async4(sa_mk, a.am.zmask + w);
+            cp_async4(sa_mk + ST4, a.am.zbase + w);
         }
     };
     auto stageB = [&](uint32_t p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
-        if (ASYNC && p < npairs) {
-            const uint32_t s0 = 2u * p;
+        if (ASYNC) {
+            const uint32_t s0 = Q * min(p, glast);
             selfB = ISLAND ? slot_lo + s0 : s0;   // global slot id
             zfB = 0u;
             if (decode) {
                 const uint32_t mA = s_mk[0][tid], bA = s_mk[1][tid];
                 const uint32_t bit = s0 & 31u;
-                const uint32_t below = mA & ((1u << bit) - 1u);
-                const uint32_t rank = bA + __popc(below);
-                const uint32_t z0 = (mA >> bit) & 1u, z1 = (mA >> (bit + 1)) & 1u;
-                if (!ISLAND) {
-                    zfB = z0 | (z1 << 1);
-                    if (z0) cp_async4(sa_sp, a.am.surplus + rank);
-                    if (z1) cp_async4(sa_sp + ST4, a.am.surplus + rank + z0);
-                } else {
-                    // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
+                const uint32_t rank = bA + __popc(mA & ((1u << bit) - 1u));
+                const uint32_t zq = (mA >> bit) & ((1u << Q) - 1u);      // the group's zero-count flags
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 0 ? z0 : z1) {
-                            const long long m = zoff_mine + rank + (h ? z0 : 0u);
+                for (int h = 0; h < Q; ++h) {
+                    if ((zq >> h) & 1u) {
+                        const uint32_t r = rank + __popc(zq & ((1u << h) - 1u));   // rank of this slot among the zero-count slots
+                        if (!ISLAND) {
+                            cp_async4(sa_sp + (unsigned)h * ST4, a.am.surplus + r);
+                            zfB |= 1u << h;
+                        } else {
+                            // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
+                            const long long m = zoff_mine + r;
                             if (m >= eoff_mine && m < eoff_next) {   // the usual case: the entry is in this island's own list
                                 cp_async4(sa_sp + (unsigned)h * ST4, a.am.surplus + (m - eoff_mine));
                                 zfB |= 1u << h;
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                                 cp_async4(sa_sp + (unsigned)h * ST4, sp + (m - a.ctrl->eoff[o]));
                                 zfB |= 1u << h;
                             } else {
-                                zfB |= 4u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
+                                zfB |= 0x100u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
                             }
                         }
                     }
@@ -221,105 +242,129 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
         }
     };
-    auto stageC = [&](uint32_t p) {   // consumes the surplus entries fetched for this p one iteration ago
-        if (ASYNC && p < npairs) {
-            const uint32_t s0 = 2u * p;
-            const bool has1 = s0 + 1u < n32;
-            uint32_t anc[2];
-            anc[0] = (zfB & 1u) ? s_sp[0][tid] : ((zfB & 4u) ? 0u : selfB);
-            anc[1] = (zfB & 2u) ? s_sp[1][tid] : ((zfB & 8u) ? 0u : selfB + 1u);
+    // stage C in two halves: the ancestors are read out of the thread's surplus slots BEFORE this iteration's stage B
+    // overwrites them, the copies of the parents' state are issued AFTER stages A/B so that they form the younger of the
+    // iteration's two cp.async groups (see the loop).
+    auto readC = [&](uint32_t (&anc)[Q]) {
+        if (ASYNC) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !has1) break;
+            for (int h = 0; h < Q; ++h)
+                anc[h] = ((zfB >> h) & 1u) ? s_sp[h][tid] : (((zfB >> (8 + h)) & 1u) ? 0u : selfB + h);
+        }
+    };
+    auto issueC = [&](const uint32_t (&anc)[Q], uint32_t p, unsigned buf) {
+        if (ASYNC) {
+            const uint32_t s0 = Q * min(p, glast);
+            const unsigned bx = sa_x + buf * XBUF, bl = sa_lw + buf * LBUF;
+#pragma unroll
+            for (int h = 0; h < Q; ++h) {   // slots past the end of a ragged last group read the arrays' alignment padding (never used)
                 if (!ISLAND) {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) cp_async8(sa_x + (unsigned)(h * D + d) * ST8, src[d] + anc[h]);
+                    for (int d = 0; d < D; ++d) cp_async8(bx + (unsigned)(h * D + d) * ST8, src[d] + anc[h]);
                 } else {
                     // the parent may live on another island: copy it from the owner's slab over NVLink
                     const uint32_t rel = anc[h] - slot_lo;
                     if (rel < (uint32_t)a.isl.n_loc) {   // the usual case under systematic / stratified resampling: a local parent
 #pragma unroll
-                        for (int d = 0; d < D; ++d) cp_async8(sa_x + (unsigned)(h * D + d) * ST8, src[d] + rel);
+                        for (int d = 0; d < D; ++d) cp_async8(bx + (unsigned)(h * D + d) * ST8, src[d] + rel);
                     } else {
                         const int o = (int)(anc[h] / (uint32_t)a.isl.n_loc);
                         const long long li = (long long)anc[h] - (long long)o * a.isl.n_loc;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const double* xs = reinterpret_cast<const double*>(a.isl.base[o] + (parity ? a.isl.off_xb[d] : a.isl.off_xa[d]));
-                            cp_async8(sa_x + (unsigned)(h * D + d) * ST8, xs + li);
+                            cp_async8(bx + (unsigned)(h * D + d) * ST8, xs + li);
                         }
                     }
                 }
-            }
-            if (!resampled) {
-                cp_async8(sa_lw, a.lw + s0);
-                if (has1) cp_async8(sa_lw + ST8, a.lw + s0 + 1);
+                if (!RES) cp_async8(bl + (unsigned)h * ST8, a.lw + s0 + h);
             }
         }
     };
-    // prologue: fill the pipeline
+    // Pipeline: iteration i works on group G_i = p0 + i S and issues, in this order,
+    //   group "AB":  stage B for G_{i+3} (rank -> surplus entries), stage A for G_{i+4} (bitmap word + rank base)
+    //   group "C":   the parents' state for G_{i+2}, into the buffer iteration i has just emptied
+    // cp.async groups complete in order, so "all but the youngest group" at the top of an iteration means: the state gathered
+    // TWO iterations ago and the small stage A/B copies of the last iteration have landed, while the last iteration's state
+    // gather may still be in flight.
     if (ASYNC) {
+        uint32_t anc[Q];
         stageA(p0); cp_async_commit(); cp_async_wait_all();
         stageB(p0); stageA(p0 + stride); cp_async_commit(); cp_async_wait_all();
-        stageC(p0); stageB(p0 + stride); stageA(p0 + 2 * stride); cp_async_commit();
+        readC(anc); stageB(p0 + stride); stageA(p0 + 2 * stride); issueC(anc, p0, 0u); cp_async_commit(); cp_async_wait_all();
+        readC(anc); stageB(p0 + 2 * stride); stageA(p0 + 3 * stride); cp_async_commit();
+        issueC(anc, p0 + stride, 1u); cp_async_commit();
     }
+    unsigned buf = 0u;
 
-    for (uint32_t p = p0; p < npairs; p += stride) {
-        const uint32_t s0 = 2u * p;
-        const bool has1 = s0 + 1u < n32;
-        double x[2][D], lwv[2];
+    auto body = [&](auto full_tag, uint32_t p) {
+        constexpr bool FULL = decltype(full_tag)::value;   // every slot of the group exists (false only for a ragged last group)
+        const uint32_t s0 = Q * p;
+        bool has[Q];
+#pragma unroll
+        for (int h = 0; h < Q; ++h) has[h] = FULL || s0 + h < n32;
+        double x[Q][D], lwv[Q];
         if (PHASE != PHASE_INIT) {
-            if (ASYNC) {   // everything issued one iteration ago has had a whole iteration to land
-                cp_async_wait_all();
+            if (ASYNC) cp_async_wait_but_youngest();
 #pragma unroll
-                for (int d = 0; d < D; ++d) { xC[0][d] = s_x[0][d][tid]; xC[1][d] = has1 ? s_x[1][d][tid] : 0.0; }
-                if (!resampled) { lwC[0] = s_lw[0][tid]; lwC[1] = has1 ? s_lw[1][tid] : 0.0; }
+            for (int h = 0; h < Q; ++h) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[h][d] = has[h] ? s_x[buf][h][d][tid] : 0.0;
+                const double lwc = (!RES && has[h]) ? s_lw[buf][h][tid] : 0.0;
+                lwv[h] = RES ? -log_n : lwc - lse_prev;
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) x[h][d] = xC[h][d];
-                lwv[h] = resampled ? -log_n : lwC[h] - lse_prev;
+            // advance the pipeline before the arithmetic of this group
+            if (ASYNC) {
+                uint32_t anc[Q];
+                readC(anc);
+                stageB(p + 3 * stride);
+                stageA(p + 4 * stride);
+                cp_async_commit();
+                issueC(anc, p + 2 * stride, buf);
+                cp_async_commit();
+                buf ^= 1u;
             }
-            // advance the pipeline before the arithmetic of this pair
-            stageC(p + stride);
-            stageB(p + 2 * stride);
-            stageA(p + 3 * stride);
-            if (ASYNC) cp_async_commit();
             if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
+                double w[Q];
+                if (RES) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {   // no early exit: the two particles' arithmetic interleaves (a missing odd tail weighs 0)
+                    for (int h = 0; h < Q; ++h) w[h] = 1.0;
+                } else {
+#pragma unroll
+                    for (int h = 0; h < Q; ++h) w[h] = fm_exp(lwv[h]);
+                }
+#pragma unroll
+                for (int h = 0; h < Q; ++h) {   // no early exit: the particles' arithmetic interleaves (a missing tail slot weighs 0)
                     double f[NOBS > 0 ? NOBS : 1];
                     Model::observe(x[h], shift, f);
-                    double w = resampled ? 1.0 : fm_exp(lwv[h]);
-                    if (h == 1) w = has1 ? w : 0.0;
-                    obs0 += w;
+                    const double wh = has[h] ? w[h] : 0.0;
+                    obs0 += wh;
 #pragma unroll
-                    for (int j = 0; j < NOBS; ++j) obs[j] = fma(w, f[j], obs[j]);
+                    for (int j = 0; j < NOBS; ++j) obs[j] = fma(wh, f[j], obs[j]);
                 }
             }
         }
         if (PHASE != PHASE_OBSERVE) {
-            // ---- standard normals: one Philox + Box-Muller per pair and draw slot, or the injected stream
-            double z[2][NZ > 0 ? NZ : 1];
+            // ---- standard normals: one Philox + Box-Muller per pair of slots and draw slot, or the injected stream
+            double z[Q][NZ > 0 ? NZ : 1];
             if (INJECT) {
-                long long off = PHASE == PHASE_INIT ? 0 : n * Model::NZ_INIT + (tcur - 1) * n * Model::NZ_MOVE;
+                const long long off = PHASE == PHASE_INIT ? 0 : n * Model::NZ_INIT + (tcur - 1) * n * Model::NZ_MOVE;
 #pragma unroll
-                for (int k = 0; k < NZ; ++k) {
-                    z[0][k] = a.znoise[off + (long long)s0 * NZ + k];
-                    z[1][k] = has1 ? a.znoise[off + ((long long)s0 + 1) * NZ + k] : 0.0;
-                }
+                for (int h = 0; h < Q; ++h)
+#pragma unroll
+                    for (int k = 0; k < NZ; ++k) z[h][k] = has[h] ? a.znoise[off + (long long)(s0 + h) * NZ + k] : 0.0;
             } else {
+                const uint64_t pair0 = (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) : 0) + (uint64_t)(Q / 2) * p;
 #pragma unroll
-                for (int k = 0; k < NZ; ++k) {
-                    if (a.dbg & 4) { z[0][k] = 0.3 + 1e-9 * (double)p; z[1][k] = -0.2; }
-                    else philox_normal2(seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur,
-                                        (uint64_t)(ISLAND ? ((a.isl.rank * a.isl.n_loc) >> 1) + p : p), k, z[0][k], z[1][k]);
-                }
+                for (int j = 0; j < Q / 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < NZ; ++k) {
+                        philox_normal2(seed, PHASE == PHASE_INIT ? STREAM_INIT : STREAM_MOVE, (uint32_t)tcur, pair0 + j, k, z[2 * j][k], z[2 * j + 1][k]);
+                    }
             }
-            double lwo[2] = {0.0, 0.0}, wo[2] = {0.0, 0.0};
+            double lwo[Q], wo[Q];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {   // straight-line for both particles: independent dependency chains
+            for (int h = 0; h < Q; ++h) {   // straight-line for all particles of the group: independent dependency chains
                 double lw;
                 if (PHASE == PHASE_INIT) {
                     Model::init(x[h], lw, prm, z[h]);   // moveset.h:133-138
@@ -331,24 +376,40 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 lwo[h] = lw;
                 double hs[G > 0 ? G : 1];
                 Model::shift_stat(x[h], hs);
-                if (h == 1) lw = has1 ? lw : -INFINITY;   // a missing odd tail contributes nothing
+                lw = has[h] ? lw : -INFINITY;              // a missing tail slot contributes nothing
                 wo[h] = acc.add(lw, cs, hs);               // the step's only exponential per particle
             }
-            if (!(a.dbg & 2)) {
-                if (has1) {   // both particles of the pair: one 16-byte store per array (s0 is even, arrays are 256-byte aligned)
+            {
+                if (FULL) {   // 16-byte stores (s0 is a multiple of Q, arrays are 256-byte aligned)
 #pragma unroll
-                    for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0) = make_double2(x[0][d], x[1][d]);
-                    *reinterpret_cast<double2*>(a.lw + s0) = make_double2(lwo[0], lwo[1]);
-                    *reinterpret_cast<double2*>(a.wt + s0) = make_double2(wo[0], wo[1]);
+                    for (int h = 0; h < Q; h += 2) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0 + h) = make_double2(x[h][d], x[h + 1][d]);
+                        *reinterpret_cast<double2*>(a.lw + s0 + h) = make_double2(lwo[h], lwo[h + 1]);
+                        *reinterpret_cast<double2*>(a.wt + s0 + h) = make_double2(wo[h], wo[h + 1]);
+                    }
                 } else {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) dst[d][s0] = x[0][d];
-                    a.lw[s0] = lwo[0];
-                    a.wt[s0] = wo[0];
+                    for (int h = 0; h < Q; ++h) {
+                        if (has[h]) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) dst[d][s0 + h] = x[h][d];
+                            a.lw[s0 + h] = lwo[h];
+                            a.wt[s0 + h] = wo[h];
+                        }
+                    }
                 }
             }
         }
+    };
+    const uint32_t nfull = n32 / Q;                 // groups in which every slot exists
+    for (uint32_t p = p0; p < ngroups; p += stride) {
+        if (p < nfull) body(std::true_type{}, p);
+        else body(std::false_type{}, p);
     }
+    };
+    if (PHASE != PHASE_INIT && resampled) run(std::true_type{});
+    else run(std::false_type{});
 
     // ---- block reduction: plain sums against the common shift (fixed order => reproducible) + the maximum log-weight
     constexpr int NF = 4 + G + NOBS;  // mx, s, q, obs0, g[G], obs[NOBS]
@@ -569,8 +630,8 @@ public:
         size_t o_t0 = take(sizeof(double) * tcap), o_t1 = take(sizeof(double) * tcap), o_t2 = take(sizeof(int) * tcap);
         size_t o_t3 = take(sizeof(double) * tcap * (NOBS > 0 ? NOBS : 1));
         size_t o_mb = take(sizeof(IslMsg) * ISL_KINDS * 2 * ISL_MAX);
-        grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
-        grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + 1) / 2, STEP_THREADS);
+        grid_init_ = persistent_grid(k_step<Model, PHASE_INIT, false>, STEP_THREADS, (n + StepShape<Model>::Q - 1) / StepShape<Model>::Q, STEP_THREADS);
+        grid_move_ = persistent_grid(k_step<Model, PHASE_MOVE, false>, STEP_THREADS, (n + StepShape<Model>::Q - 1) / StepShape<Model>::Q, STEP_THREADS);
         grid_scan_ = resample_pass_grid(n);
         int gmax = grid_init_ > grid_move_ ? grid_init_ : grid_move_;
         size_t o_pa = take(sizeof(double) * (size_t)(4 + G + NOBS) * gmax);

@@ -42,7 +42,7 @@ struct NonlinBS {
     __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {  // :106-109
         const double std_x = 3.1622776601683795;
         double v = x[0];
-        v = 0.5 * v + 25.0 * v / (1.0 + v * v) + p.cterm[t] + (0.0 + std_x * z[0]);
+        v = 0.5 * v + fm_div(25.0 * v, 1.0 + v * v) + p.cterm[t] + (0.0 + std_x * z[0]);   // 1 + v^2 >= 1: the branch-free correctly rounded quotient
         x[0] = v;
         lw += loglik(p, t, v);
     }
@@ -136,7 +136,7 @@ struct NonlinPMMH {
     }
     __device__ static __forceinline__ void move(long long t, double (&x)[D], double& lw, const Params& p, const double* z) {  // :181-186
         double v = x[0];
-        v = v / 2.0 + 25.0 * v / (1 + v * v) + p.cterm[t] + (0.0 + p.sigv * z[0]);
+        v = v / 2.0 + fm_div(25.0 * v, 1 + v * v) + p.cterm[t] + (0.0 + p.sigv * z[0]);
         x[0] = v;
         lw += dnorm_log(p.y[t], (v * v) / 20.0, p);
     }
