@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-for v in nolw nolwwt; do SMCB200_LIB=build/libsmcb200_$v.so timeout 120 python scripts/ab_time.py 24 100 3; done 2>&1 | tee gpurun_out/r2b_ab.log
+timeout 120 python scripts/prof_target.py 24 6 > gpurun_out/r2b_plain.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 2 -c 1 -f -o gpurun_out/r2d_step python scripts/prof_target.py 24 6 > gpurun_out/r2b_ncu.log 2>&1
+tail -n 2 gpurun_out/r2b_ncu.log
