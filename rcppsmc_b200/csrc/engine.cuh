@@ -113,6 +113,10 @@ __device__ __forceinline__ void cp_async4(unsigned smem, const void* g) {
 __device__ __forceinline__ void cp_async8(unsigned smem, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(g) : "memory");
 }
+// 256-bit store (sm_100): four consecutive doubles, 32-byte aligned
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_youngest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -380,13 +384,20 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 wo[h] = acc.add(lw, cs, hs);               // the step's only exponential per particle
             }
             {
-                if (FULL) {   // 16-byte stores (s0 is a multiple of Q, arrays are 256-byte aligned)
+                if (FULL) {   // one 32-byte store per array for Q = 4 (s0 is a multiple of Q, arrays are 256-byte aligned): whole sectors
+                    if (Q == 4) {
 #pragma unroll
-                    for (int h = 0; h < Q; h += 2) {
+                        for (int d = 0; d < D; ++d) st_global_v4(dst[d] + s0, x[0][d], x[1][d], x[2][d], x[3][d]);
+                        st_global_v4(a.lw + s0, lwo[0], lwo[1], lwo[2], lwo[3]);
+                        st_global_v4(a.wt + s0, wo[0], wo[1], wo[2], wo[3]);
+                    } else {
 #pragma unroll
-                        for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0 + h) = make_double2(x[h][d], x[h + 1][d]);
-                        *reinterpret_cast<double2*>(a.lw + s0 + h) = make_double2(lwo[h], lwo[h + 1]);
-                        *reinterpret_cast<double2*>(a.wt + s0 + h) = make_double2(wo[h], wo[h + 1]);
+                        for (int h = 0; h < Q; h += 2) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(dst[d] + s0 + h) = make_double2(x[h][d], x[h + 1][d]);
+                            *reinterpret_cast<double2*>(a.lw + s0 + h) = make_double2(lwo[h], lwo[h + 1]);
+                            *reinterpret_cast<double2*>(a.wt + s0 + h) = make_double2(wo[h], wo[h + 1]);
+                        }
                     }
                 } else {
 #pragma unroll

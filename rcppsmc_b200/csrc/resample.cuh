@@ -244,10 +244,10 @@ __device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long l
             // ceil((W - u) N) clamped to [0, N].  The scaling is exact; adding 1.5 * 2^52 rounds to the nearest integer and leaves
             // it, in two's complement, in the low word (valid for |g| < 2^31: g > -1 and N <= 2^30 here), so the clamps are two
             // integer min/max instead of two fp64 ones.
-            const double g = (W - dRand) * nd;
-            const double t = g + 6755399441055744.0;
-            const double r = t - 6755399441055744.0;
-            const int c = __double2loint(t) + (r < g ? 1 : 0);
+            // N = 2^b: scaling commutes with rounding, so one fused multiply-add gives fl(W - u) N exactly; adding 1.5 * 2^52
+            // ROUNDING UP leaves ceil(g) in the low word (two's complement; valid for -1 < g < 2^31), no compare needed
+            const double g = fma(W, nd, -(dRand * nd));
+            const int c = __double2loint(__dadd_ru(g, 6755399441055744.0));
             return min(max(c, 0), (int)nthr);
         }
         return (int)children_below(W - dRand, nthr, nd, false);
@@ -653,6 +653,19 @@ constexpr int RP_SUPER = 128;                   // tiles per super
 constexpr int RP_THREADS = 256;
 static_assert(RP_TILE == 256, "scan_tiles() sizes the per-tile arrays for 256-slot tiles");
 
+// 256-bit global accesses (sm_100): every lane moves one whole 32-byte sector
+__device__ __forceinline__ void ld_global_v4(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const uint32_t* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 enum { SRC_WTILDE = 2 };   // weights exp(lw - c) against a step-wide shift c, normalised by one multiplication (k_step writes them)
 
 struct RsView {            // how the three passes see the workspace of ScanArgs
@@ -773,9 +786,8 @@ __device__ __forceinline__ void rs_count_body(const ScanArgs& a) {
     auto load_tile = [&](int t, double (&r)[RP_ITEMS]) {
         const int g = t * RP_TILE + lane * RP_ITEMS;
         if (g + RP_ITEMS <= n32) {
-            const double2* p = reinterpret_cast<const double2*>(a.in + g);
-#pragma unroll
-            for (int k = 0; k < RP_ITEMS / 2; ++k) { const double2 v = p[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+            ld_global_v4(a.in + g, r[0], r[1], r[2], r[3]);
+            ld_global_v4(a.in + g + 4, r[4], r[5], r[6], r[7]);
         } else {
 #pragma unroll
             for (int k = 0; k < RP_ITEMS; ++k) r[k] = g + k < n32 ? a.in[g + k] : 0.0;
@@ -820,9 +832,7 @@ __device__ __forceinline__ void rs_count_body(const ScanArgs& a) {
         }
         zbits &= (1u << nv) - 1u;
         // c is padded to whole tiles, so the stores need no guard
-        uint4* cp = reinterpret_cast<uint4*>(a.cslot + g0);
-        cp[0] = make_uint4(c[0], c[1], c[2], c[3]);
-        cp[1] = make_uint4(c[4], c[5], c[6], c[7]);
+        st_global_v8(a.cslot + g0, c);
         {   // zero-slot bitmap: 4 lanes x 8 slots = one 32-bit word
             unsigned m = zbits << (8 * (lane & 3));
             m |= __shfl_xor_sync(SMCB_FULL, m, 1);
@@ -883,10 +893,10 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
             const int nv = min(max(n32 - g0, 0), RP_ITEMS);
             int c[RP_ITEMS];
             {
-                const uint4* cp = reinterpret_cast<const uint4*>(a.cslot + g0);
-                const uint4 u = cp[0], v = cp[1];
-                c[0] = (int)u.x; c[1] = (int)u.y; c[2] = (int)u.z; c[3] = (int)u.w;
-                c[4] = (int)v.x; c[5] = (int)v.y; c[6] = (int)v.z; c[7] = (int)v.w;
+                uint32_t u[8];
+                ld_global_v8(a.cslot + g0, u);
+#pragma unroll
+                for (int k = 0; k < RP_ITEMS; ++k) c[k] = (int)u[k];
             }
             int cfirst = __shfl_up_sync(SMCB_FULL, c[RP_ITEMS - 1], 1);
             if (lane == 0) cfirst = clast;
@@ -939,24 +949,26 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
                     const int wlen = min(etile - w0, RP_WINDOW);
                     for (int j = lane; j < wlen; j += 32) seg[j] = 0u;
                     __syncwarp();
+                    if (etile <= RP_WINDOW) {   // the usual case, one window: every run starts inside it
 #pragma unroll
-                    for (int k = 0; k < RP_ITEMS; ++k) {
-                        const int pos = lane_off + o[k] - w0;
-                        if (cnt[k] > 1 && pos >= 0 && pos < wlen) seg[pos] = (uint32_t)(lane * RP_ITEMS + k + 1);
+                        for (int k = 0; k < RP_ITEMS; ++k) if (cnt[k] > 1) seg[lane_off + o[k]] = (uint32_t)(lane * RP_ITEMS + k + 1);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RP_ITEMS; ++k) {
+                            const int pos = lane_off + o[k] - w0;
+                            if (cnt[k] > 1 && pos >= 0 && pos < wlen) seg[pos] = (uint32_t)(lane * RP_ITEMS + k + 1);
+                        }
                     }
                     __syncwarp();
+                    uint32_t* out = a.am.surplus + (Etile + w0);   // the list cannot overflow: a rank's entries <= children handed out <= N
                     for (int j0 = 0; j0 < wlen; j0 += 32) {
                         const int j = j0 + lane;
                         uint32_t v = j < wlen ? seg[j] : 0u;
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const uint32_t t = __shfl_up_sync(SMCB_FULL, v, d);
-                            if (lane >= d) v = max(v, t);
-                        }
+                        for (int d = 1; d < 32; d <<= 1) v = max(v, __shfl_up_sync(SMCB_FULL, v, d));   // lanes below d get their own value back
                         v = max(v, carry);
                         carry = __shfl_sync(SMCB_FULL, v, 31);
-                        const long long m = Etile + w0 + j;
-                        if (j < wlen && m < scap) a.am.surplus[m] = id0 + v - 1u;
+                        if (j < wlen) out[j] = id0 + v - 1u;
                     }
                     __syncwarp();
                 }
