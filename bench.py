@@ -139,13 +139,26 @@ def cpu_time_filter(kind, L, y, n, t):
                                   ctypes.c_ulonglong(1))
 
 
+def host_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"host_cpus": os.cpu_count(), "host_cpu_model": model}
+
+
 def cpu_baseline(y, log2n=LOG2_N, t=2):
     kind, L = cpu_lib()
     n = 1 << log2n
     sec = cpu_time_filter(kind, L, y, n, t)
-    return {"value": n * t / sec, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+    return dict({"value": n * t / sec, "unit": "particle-steps/s", "cores": 1, "kind": kind,
             "sample": f"pfNonlinBS 2^{log2n} particles x {t} steps, systematic resampling every step, 1 thread "
-                      f"({'reference smc::sampler compiled from its own sources, shim RNG' if kind == 'reference' else 'C port of the reference path'}), {sec:.1f} s"}
+                      f"({'reference smc::sampler compiled from its own sources, shim RNG' if kind == 'reference' else 'C port of the reference path'}), {sec:.1f} s"},
+                **host_info())
 
 
 def run_reference_arm(args):
@@ -172,8 +185,9 @@ def run_reference_arm(args):
             "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (restated simNonlin, fixed seed)",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": kind, "sample": sample},
+            "config": dict(workload_config(args.gpus), reference_sample={"particles": n, "time_steps": t_s,
+                           "note": "the CPU path is linear in particles x steps; the rate is per particle-step"}),
+            "cpu_baseline": dict({"value": value, "unit": "particle-steps/s", "cores": 1, "kind": kind, "sample": sample}, **host_info()),
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -187,6 +201,42 @@ def workload_config(gpus):
             "parallelism": "1 GPU" if gpus == 1 else f"island partition: one population of {gpus} x 2^{LOG2_N} particles, global systematic "
                            f"resampling, per-step all-gathers and remote parent reads inside the kernels over NVLink peer memory (CUDA IPC)",
             "l2": "working set per step (>= 400 MB of state, weights and ancestor lists) exceeds the 126 MB L2; no explicit flush"}
+
+
+def verify_island(smc, dist, torch, rank, world, local, stream, log2n_total=20, T=10):
+    """Before anything is timed: a short island run (2^20 particles in total x 10 steps) must reproduce the single-GPU run of
+    the same population -- traces to 1e-9 relative and the last step's ancestor indices bit for bit."""
+    from rcppsmc_b200 import island
+    n_glob = 1 << log2n_total
+    n_loc = n_glob // world
+    y = synthetic_data(T, seed=7)
+    f = smc.PfNonlinBS(n_loc, T, seed=4242, stream=stream.cuda_stream, island=(rank, world))
+    island.connect(f, device=torch.device("cuda", local))
+    f.set_data(y)
+    f.run(SYSTEMATIC)
+    f.sync()
+    out = f.read()
+    anc = torch.from_numpy(f.read_ancestors().astype(np.int64)).cuda()
+    parts = [torch.empty_like(anc) for _ in range(world)]
+    dist.all_gather(parts, anc)
+    res = torch.zeros(6, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        g = smc.PfNonlinBS(n_glob, T, seed=4242, stream=stream.cuda_stream)
+        g.set_data(y)
+        g.run(SYSTEMATIC)
+        g.sync()
+        ref = g.read()
+        ref_anc = g.read_ancestors().astype(np.int64)
+        g.close()
+        err = [float(np.max(np.abs(out[k] - ref[k]) / np.maximum(1e-12, np.abs(ref[k])))) for k in ("logNC", "ESS", "mean", "sd")]
+        anc_ok = bool(np.array_equal(torch.cat(parts).cpu().numpy(), ref_anc))
+        ok = anc_ok and max(err) <= 1e-9 and bool(np.array_equal(out["resampled"], ref["resampled"]))
+        res = torch.tensor([1.0 if ok else 0.0, 1.0 if anc_ok else 0.0] + err, dtype=torch.float64, device="cuda")
+    dist.broadcast(res, 0)
+    f.close()
+    r = res.cpu().numpy()
+    return {"ok": bool(r[0] == 1.0), "ancestors_bit_exact": bool(r[1] == 1.0), "particles_total": n_glob, "time_steps": T,
+            "max_rel_err": {"logNC": float(r[2]), "ESS": float(r[3]), "mean": float(r[4]), "sd": float(r[5])}}
 
 
 def main():
@@ -231,8 +281,18 @@ def main():
         f = smc.PfNonlinBS(n, T_STEPS, seed=1000, stream=stream.cuda_stream, island=(rank, world))
         island.connect(f, device=torch.device("cuda", local))   # 64-byte IPC handles over the NCCL group: plumbing only
     trace("handles connected")
+    island_check = None
+    if world > 1:
+        island_check = verify_island(smc, dist, torch, rank, world, local, stream)
+        trace(f"island check {island_check}")
+        if not island_check["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "island run does not reproduce the single-GPU run", "check": island_check}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            return 3
     f.set_data(y)
-    f.set_profile(world == 1)
+    f.set_profile(False)
 
     def barrier():
         if dist is not None:
@@ -258,10 +318,13 @@ def main():
     barrier()
     trace("timed region done")
     ms = e0.elapsed_time(e1)
-    if world == 1:
-        move_ms, move_n, scan_ms, scan_n = f.kernel_ms()  # per-kernel events of the last timed step
     launches = f.launches() * args.steps
     out_dev = f.read()
+    if world == 1:   # kernel split: one extra, untimed filter with an event after every launch
+        f.set_profile(True)
+        f.run(SYSTEMATIC)
+        f.sync()
+        move_ms, move_n, scan_ms, scan_n = f.kernel_ms()
 
     # ---- end to end through the public call: host buffers in, host buffers out, every step
     f.set_profile(False)
@@ -293,12 +356,12 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         if world == 1:
-            dominant = "k_step (gather + propagate + weight)" if move_ms >= scan_ms else "k_resample_scan (normalise + scan + ancestor map)"
+            dominant = "k_step (gather + propagate + weight)" if move_ms >= scan_ms else "resampling passes (k_rs_mass + k_rs_count + k_rs_map)"
             per_launch_ms = (move_ms / max(1, move_n)) if move_ms >= scan_ms else (scan_ms / max(1, scan_n))
             alg_bytes = (ALG_BYTES_MOVE if move_ms >= scan_ms else ALG_BYTES_SCAN) * n
-            tkey = "k_step" if move_ms >= scan_ms else "k_resample_scan"
+            tkey = "k_step" if move_ms >= scan_ms else "k_rs"
         else:   # per-kernel events are a single-GPU diagnostic: report the whole step per GPU instead
-            dominant = "whole step per GPU (k_step + k_mass_total + k_resample_scan)"
+            dominant = "whole step per GPU (k_step + k_rs_mass + k_rs_count + k_rs_map)"
             per_launch_ms = ms_max / args.steps / T_STEPS
             alg_bytes = ALG_BYTES_PER_PSTEP * n
             tkey = None
@@ -307,7 +370,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (traffic or {}).get(tkey) if tkey else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms,
-                    "step_share": {"k_step_ms": move_ms, "k_resample_scan_ms": scan_ms, "filter_ms": ms_max / args.steps},
+                    "step_share": {"k_step_ms": move_ms, "resampling_passes_ms": scan_ms, "filter_ms": ms_max / args.steps,
+                                   "note": "per-launch CUDA events of one extra, untimed filter"},
                     "whole_path": {"achieved": value / world * ALG_BYTES_PER_PSTEP / 1e9, "frac": value / world * ALG_BYTES_PER_PSTEP / 1e9 / peak,
                                    "bytes_per_particle_step": ALG_BYTES_PER_PSTEP}}
         cpu = None if args.no_cpu else cpu_baseline(y)
@@ -318,10 +382,11 @@ def main():
                 "config": workload_config(world), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(2 * 8 * T_STEPS),
                         "d2h_bytes_per_step": int((4 * 8 + 4) * T_STEPS),
-                        "note": "smcb200_pfNonlinBS one-shot C-ABI call with host buffers (observations in, mean/sd/logNC/ESS/resampled out)"},
+                        "note": ("smcb200_pfNonlinBS one-shot C-ABI call with host buffers (observations in, mean/sd/logNC/ESS/resampled out)" if world == 1 else
+                                 "island handle, per step: smcb200_pfNonlinBS_set_data (observations host -> device), _run, _read (traces device -> host)")},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "check": {"logNC_final": float(out_dev["logNC"][-1]), "mean_final": float(out_dev["mean"][-1]),
-                          "e2e_logNC_final": float(out_e2e["logNC"][-1])}}
+                          "e2e_logNC_final": float(out_e2e["logNC"][-1]), "island_vs_single_gpu": island_check}}
         print(json.dumps(line), flush=True)
     f.close()
     if dist is not None:

@@ -39,6 +39,9 @@ int smcb200_device_count(void);
 
 /* Philox4x32-10 block function (known-answer surface for the RNG that replaces R's; host computation). */
 int smcb200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* The same function evaluated by a kernel (the device build of the round function): n blocks of (ctr[4], key[2]) in,
+ * n blocks of 4 words out.  Known-answer tests of the device path. */
+int smcb200_philox4x32_device(const uint32_t* ctr_key_host, long n, uint32_t* out_host);
 
 /* n standard normals exactly as the engine draws them for (seed, stream, step): particle i gets out[i].
  * Runs on the device. */

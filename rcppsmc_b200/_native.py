@@ -40,6 +40,7 @@ def lib():
     L.smcb200_version.restype = ctypes.c_int
     L.smcb200_device_count.restype = ctypes.c_int
     L.smcb200_philox4x32.argtypes = [_c_u32_p, _c_u32_p, _c_u32_p]
+    L.smcb200_philox4x32_device.argtypes = [_c_u32_p, ctypes.c_long, _c_u32_p]
     L.smcb200_philox_normals.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_long, _c_double_p]
     L.smcb200_lse.argtypes = [_c_double_p, ctypes.c_long, _c_double_p]
     L.smcb200_fastmath_eval.argtypes = [ctypes.c_int, _c_double_p, ctypes.c_long, _c_double_p]
@@ -116,6 +117,14 @@ def philox4x32(ctr, key):
     k = np.asarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
     _check(lib().smcb200_philox4x32(c.ctypes.data_as(_c_u32_p), k.ctypes.data_as(_c_u32_p), out.ctypes.data_as(_c_u32_p)))
+    return out
+
+
+def philox4x32_device(ctr_key):
+    """Philox4x32-10 evaluated by a kernel: rows of (ctr0..3, key0..1) -> rows of 4 output words."""
+    ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)
+    out = np.zeros((ck.shape[0], 4), dtype=np.uint32)
+    _check(lib().smcb200_philox4x32_device(ck.ctypes.data_as(_c_u32_p), ck.shape[0], out.ctypes.data_as(_c_u32_p)))
     return out
 
 

@@ -59,6 +59,15 @@ __global__ void k_philox_normals(unsigned long long seed, uint32_t stream, uint3
     if (2 * p + 1 < n) out[2 * p + 1] = z1;
 }
 
+// Philox4x32-10 evaluated ON THE DEVICE (the __umulhi path of philox.cuh) for known-answer tests
+__global__ void k_philox_raw(const uint32_t* ctr_key, int n, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    Philox::rand4(ctr_key[6 * i], ctr_key[6 * i + 1], ctr_key[6 * i + 2], ctr_key[6 * i + 3], ctr_key[6 * i + 4], ctr_key[6 * i + 5], o);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = o[k];
+}
+
 __global__ void k_fastmath(int fn, const double* in, long long n, double* out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -107,6 +116,19 @@ int smcb200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     Philox::rand4(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);
     for (int i = 0; i < 4; ++i) out[i] = o[i];
     return SMCB200_OK;
+}
+
+int smcb200_philox4x32_device(const uint32_t* ctr_key_host, long n, uint32_t* out_host) {
+    return guarded([&]() -> int {
+        if (n < 1 || !ctr_key_host || !out_host) throw std::invalid_argument("smcb200_philox4x32_device: n >= 1, inputs and out required");
+        require_device();
+        DevBuf in(sizeof(uint32_t) * 6 * n), out(sizeof(uint32_t) * 4 * n);
+        SMCB_CUDA(cudaMemcpy(in.p, ctr_key_host, sizeof(uint32_t) * 6 * n, cudaMemcpyHostToDevice));
+        k_philox_raw<<<(unsigned)((n + 127) / 128), 128>>>(in.as<uint32_t>(), (int)n, out.as<uint32_t>());
+        SMCB_CUDA(cudaGetLastError());
+        SMCB_CUDA(cudaMemcpy(out_host, out.p, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost));
+        return SMCB200_OK;
+    });
 }
 
 int smcb200_philox_normals(uint64_t seed, uint32_t stream, uint32_t step, long n, double* out_host) {
@@ -342,7 +364,8 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
         for (long t = 1; t < h->T; ++t) s.Iterate();
         s.ObserveFinal();
         SMCB_CUDA(cudaEventRecord(h->ev1, h->stream));
-        h->launches = h->T * (s.island() ? 3 : (resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 2 : 4) + 1;
+        // per step: k_step + the three resampling passes (mass / count / map), or + the four kernels of the draw-based schemes
+        h->launches = h->T * ((resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 4 : 5) + 1;
         h->ran = true;
         return SMCB200_OK;
     });
@@ -412,23 +435,18 @@ int smcb200_pfNonlinBS_kernel_ms(smcb200_pf* h, float* move_ms, long* move_launc
         if (!h->ran || !h->profile || h->kev_used < 3) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: run with profiling enabled first");
         if (h->mode != SMCB200_SYSTEMATIC && h->mode != SMCB200_STRATIFIED) throw std::runtime_error("smcb200_pfNonlinBS_kernel_ms: per-kernel split is defined for SYSTEMATIC / STRATIFIED runs");
         SMCB_CUDA(cudaEventSynchronize(h->kev[h->kev_used - 1]));
-        // launch order: init, scan, (move, scan) x (T-1), observe; interval i lies between events i and i+1.
-        // Island mode has a weight-mass pass in front of every scan (init, mass, scan, (move, mass, scan) x (T-1), observe);
-        // it is reported as part of the scan time, and separately on stderr when SMCB200_PROF_PRINT is set.
-        double mv = 0, sc = 0, mass = 0; long nm = 0, ns = 0;
+        // event order: init, passes, (move, passes) x (T-1), observe; interval i lies between events i and i+1 ("passes" = the
+        // three resampling kernels of a step, timed together)
+        double mv = 0, sc = 0; long nm = 0, ns = 0;
         const size_t nint = h->kev_used - 1;
-        const bool isl = h->s->island();
         for (size_t i = 0; i < nint; ++i) {
             float ms; SMCB_CUDA(cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]));
             if (i == 0 || i == nint - 1) continue;           // init and the final moment pass are not counted
-            if (!isl) { if (i % 2 == 1) { sc += ms; ++ns; } else { mv += ms; ++nm; } }
-            else if (i % 3 == 1) { sc += ms; mass += ms; }
-            else if (i % 3 == 2) { sc += ms; ++ns; }
-            else { mv += ms; ++nm; }
+            if (i % 2 == 1) { sc += ms; ++ns; } else { mv += ms; ++nm; }
         }
-        if (isl && getenv("SMCB200_PROF_PRINT"))
-            fprintf(stderr, "[smcb200] island rank %d: k_step %.1f us, k_mass_total %.1f us, k_resample_scan %.1f us per step\n", h->s->rank(),
-                    1e3 * mv / (nm ? nm : 1), 1e3 * mass / (ns ? ns : 1), 1e3 * (sc - mass) / (ns ? ns : 1));
+        if (h->s->island() && getenv("SMCB200_PROF_PRINT"))
+            fprintf(stderr, "[smcb200] island rank %d: k_step %.1f us, resampling passes %.1f us per step\n", h->s->rank(),
+                    1e3 * mv / (nm ? nm : 1), 1e3 * sc / (ns ? ns : 1));
         *move_ms = (float)mv; *move_launches = nm; *scan_ms = (float)sc; *scan_launches = ns;
         return SMCB200_OK;
     });

@@ -13,6 +13,7 @@
 // (population.h:53-112) is never materialised on the device.
 #pragma once
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <type_traits>
 #include <vector>
@@ -590,6 +591,27 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     }
 }
 
+// uRSIndices of this island's slots as GLOBAL parent ids (island mode): the same decode as stage B / C of k_step, including
+// surplus entries that live in another island's list (read over NVLink peer memory).
+static __global__ void k_decode_indices_island(AncestorMap am, long long n_loc, const Ctrl* ctrl, IslandInfo isl, uint32_t* idx) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_loc) return;
+    const uint32_t slot_lo = (uint32_t)(isl.rank * isl.n_loc);
+    const uint32_t word = am.zmask[s >> 5], bit = (uint32_t)s & 31u;
+    uint32_t anc = slot_lo + (uint32_t)s;
+    if ((word >> bit) & 1u) {
+        const long long m = ctrl->zoff[isl.rank] + am.zbase[s >> 5] + __popc(word & ((1u << bit) - 1u));
+        if (m >= ctrl->eoff[isl.world]) anc = 0u;   // beyond the available surplus children: particle 0 (sampler.h:845)
+        else {
+            int o = 0;
+            while (o + 1 < isl.world && m >= ctrl->eoff[o + 1]) ++o;
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(isl.base[o] + isl.off_surplus);
+            anc = sp[m - ctrl->eoff[o]];
+        }
+    }
+    idx[s] = anc;
+}
+
 // Number of persistent blocks for a kernel: all SMs x resident blocks, capped by the work available.
 template <class K>
 inline int persistent_grid(K kernel, int threads, long long work_items, int items_per_block) {
@@ -699,6 +721,11 @@ public:
 
     // sampler.h:885-893
     void SetResampleParams(int mode, double threshold) {
+        if (mode < MULTINOMIAL || mode > SYSTEMATIC) throw std::invalid_argument("unknown resampling mode");
+        // rejected here, before anything is launched: a rank that throws in the middle of a step would leave its peers
+        // spinning on the in-kernel all-gathers
+        if (island() && mode != SYSTEMATIC && mode != STRATIFIED)
+            throw std::invalid_argument("island mode supports SYSTEMATIC and STRATIFIED resampling");
         mode_ = mode;
         thr_ = threshold < 1 ? threshold * (double)n_glob_ : threshold;
     }
@@ -751,7 +778,9 @@ public:
     // occupancy queries), the graph is rebuilt when the resampling mode, length or injected-draw pointers change.
     // Returns with the filter finished when it was replayed from a graph; an eager run is only enqueued.
     void RunFilter(long long T, bool use_graph = true) {
-        const GraphKey key{mode_, T, znoise_, ures_, ustrat_, udraw_};
+        GraphKey key{mode_, T, znoise_, ures_, ustrat_, udraw_, {}};
+        static_assert(sizeof(typename Model::Params) <= sizeof(key.params), "GraphKey::params too small for this model");
+        std::memcpy(key.params, &params_, sizeof(typename Model::Params));   // kernel arguments are baked into the captured nodes
         const bool have = graph_exec_ && key == graph_key_;
         if (!use_graph || island() || after_launch_ || (!have && !(graph_warm_ && key == warm_key_))) {
             Initialise();   // first filter of this shape: eager (lazy allocations and occupancy queries happen here)
@@ -823,12 +852,13 @@ public:
         Ctrl c = ReadCtrl();
         uint32_t* d = dalloc_tmp<uint32_t>(n_);
         if (c.resampled) {
-            k_decode_indices<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, d);
+            if (island()) k_decode_indices_island<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, ctrl_, isl_, d);
+            else k_decode_indices<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, d);
             SMCB_CUDA(cudaGetLastError());
             SMCB_CUDA(cudaMemcpyAsync(host_idx, d, sizeof(uint32_t) * n_, cudaMemcpyDeviceToHost, stream_));
             Sync();
         } else {
-            for (long long i = 0; i < n_; ++i) host_idx[i] = (uint32_t)i;
+            for (long long i = 0; i < n_; ++i) host_idx[i] = (uint32_t)(rank_ * n_ + i);   // global ids (island mode: rank offset)
         }
         cudaFree(d);
     }
@@ -840,7 +870,10 @@ public:
 private:
     struct GraphKey {
         int mode; long long T; const double* z; const double* u0; const double* u1; const double* u2;
-        bool operator==(const GraphKey& o) const { return mode == o.mode && T == o.T && z == o.z && u0 == o.u0 && u1 == o.u1 && u2 == o.u2; }
+        unsigned char params[96];
+        bool operator==(const GraphKey& o) const {
+            return mode == o.mode && T == o.T && z == o.z && u0 == o.u0 && u1 == o.u1 && u2 == o.u2 && std::memcmp(params, o.params, sizeof params) == 0;
+        }
     };
     Ctrl fresh_ctrl() const {
         Ctrl h{};

@@ -23,4 +23,4 @@ def test_island_matches_single_gpu(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("-> OK") == 2
+    assert r.stdout.count("-> OK") == 4
