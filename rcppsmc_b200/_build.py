@@ -23,17 +23,38 @@ def stale():
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
 
 
+def _compile_objects(flags, obj_dir, sources, force, verbose):
+    """One nvcc per translation unit, all at once (the units are independent: no relocatable device code), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    newest_header = max(os.path.getmtime(f) for f in HEADERS)
+    jobs = []
+    for src in sources:
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append((src, obj))
+    def run(job):
+        cmd = [nvcc] + [f for f in flags if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", job[1], job[0]]
+        return job, subprocess.run(cmd, capture_output=True, text=True)
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for job, r in ex.map(run, jobs):
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed compiling " + job[0])
+            if verbose:
+                sys.stderr.write(r.stderr)
+    return [os.path.join(obj_dir, os.path.basename(src) + ".o") for src in sources]
+
+
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objs = _compile_objects(NVCC_FLAGS, os.path.join(ROOT, ".objcache", "main"), SOURCES, force, verbose)
+    r = subprocess.run([os.environ.get("NVCC", "nvcc"), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libsmcb200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libsmcb200.so")
     return LIB
 
 
@@ -42,11 +63,11 @@ def build_variant(name, defines):
     out_dir = os.path.join(ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libsmcb200_{name}.so")
-    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SOURCES
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objs = _compile_objects(NVCC_FLAGS + [f"-D{d}" for d in defines], os.path.join(ROOT, ".objcache", name), SOURCES, True, False)
+    r = subprocess.run([os.environ.get("NVCC", "nvcc"), "-shared", "-o", out] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError(f"nvcc failed building {out}")
+        raise RuntimeError(f"nvcc failed linking {out}")
     return out
 
 

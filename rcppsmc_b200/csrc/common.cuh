@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
@@ -23,6 +24,27 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define SMCB_CUDA(x) ::smcb::cuda_check((x), #x, __FILE__, __LINE__)
+
+// Programmatic dependent launch (sm_90+): the kernels of a filter step form a chain in one stream; launched with this helper,
+// the blocks of the next kernel are scheduled onto the SMs while the previous kernel drains, and wait in
+// pdl_wait_for_predecessor() until all of its memory is visible -- the launch latency between dependent kernels
+// disappears.  A kernel launched the ordinary way passes both calls as no-ops.  Disabled with SMCB200_NO_PDL=1.
+__device__ __forceinline__ void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release_successor() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SMCB200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <class... KArgs, class... Args>
+inline void launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SMCB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
 
 // Resampling modes / history modes: numeric values are the reference's (inst/include/sampler.h:45-68).
 enum ResampleMode : int { MULTINOMIAL = 0, RESIDUAL = 1, STRATIFIED = 2, SYSTEMATIC = 3 };

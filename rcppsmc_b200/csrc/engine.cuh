@@ -120,7 +120,7 @@ __device__ __forceinline__ void st_global_v4(double* p, double a, double b, doub
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_youngest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_two() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
 template <class Model, int PHASE, bool INJECT, bool ISLAND = false>
 __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     constexpr int NZ = PHASE == PHASE_INIT ? Model::NZ_INIT : Model::NZ_MOVE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n = a.n;
+    pdl_wait_for_predecessor();   // everything below reads what the previous kernel of the stream wrote
+    pdl_release_successor();      // the next kernel's blocks may take the SMs as this grid's blocks retire
 
     // ---- snapshot of the control block (stable until the last block's finalize)
     const long long T = a.ctrl->T;
@@ -163,9 +165,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     // chains per thread hide the fp64 latency, one Philox call + one Box-Muller per two slots, and the four slots share one
     // bitmap word of the ancestor map).  The ancestor decode is a chain of three dependent loads (bitmap word -> surplus entry
     // -> parent state), so each link is issued one iteration ahead of its use:
-    //   stage A (group p+4S)  bitmap word + rank base          stage B (group p+3S)  rank -> surplus loads
+    //   stage A (group p+6S)  bitmap word + rank base          stage B (group p+4S)  rank -> surplus loads
     //   stage C (group p+2S)  parent state (and stored log-weight when the last step did not resample)
     //   compute (group p)     moments, RNG, model functor, stores, weight sums
+    // Every link is consumed TWO iterations after it was issued (measured with one iteration of lead for the two small links:
+    // 23 % of the warp stall samples sat on the wait for them, profiles/r2c_kernels.txt).
     // 32-bit group / slot indices inside the loop (n < 2^31): half the integer work of 64-bit index arithmetic
     constexpr int Q = StepShape<Model>::Q;
     const uint32_t n32 = (uint32_t)n;
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     // of freshly issued gathers whenever a register of an older, finished load was recycled.  In island mode the source of a
     // copy may be a peer's slab (surplus entry or parent state on another island): same instruction, NVLink underneath.
     constexpr bool ASYNC = PHASE != PHASE_INIT;
-    __shared__ uint32_t s_mk[2][ASYNC ? STEP_THREADS : 1];      // bitmap word, rank base
-    __shared__ uint32_t s_sp[Q][ASYNC ? STEP_THREADS : 1];      // surplus entries of the group
+    __shared__ uint32_t s_mk[2][2][ASYNC ? STEP_THREADS : 1];   // [iteration parity][bitmap word, rank base]
+    __shared__ uint32_t s_sp[2][Q][ASYNC ? STEP_THREADS : 1];   // [iteration parity] surplus entries of the group
     __shared__ double s_x[2][Q][D][ASYNC ? STEP_THREADS : 1];   // parents' state, double-buffered (gathered two iterations ahead)
     __shared__ double s_lw[2][Q][ASYNC ? STEP_THREADS : 1];     // stored log-weights (no resampling last step), likewise
     // The loop exists in two versions, selected by one uniform branch: after a resampling step (ancestor decode, uniform
@@ -189,72 +193,79 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     constexpr bool RES = decltype(res_tag)::value;
     constexpr bool decode = PHASE != PHASE_INIT && RES;
     // the thread's slots: array k of a family sits k * stride bytes after the first one
-    const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][ASYNC ? tid : 0]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][ASYNC ? tid : 0]);
+    const unsigned sa_mk = (unsigned)__cvta_generic_to_shared(&s_mk[0][0][ASYNC ? tid : 0]), sa_sp = (unsigned)__cvta_generic_to_shared(&s_sp[0][0][ASYNC ? tid : 0]);
     const unsigned sa_x = (unsigned)__cvta_generic_to_shared(&s_x[0][0][0][ASYNC ? tid : 0]), sa_lw = (unsigned)__cvta_generic_to_shared(&s_lw[0][0][ASYNC ? tid : 0]);
     constexpr unsigned ST4 = STEP_THREADS * 4u, ST8 = STEP_THREADS * 8u;
     constexpr unsigned XBUF = (unsigned)(Q * D) * ST8, LBUF = (unsigned)Q * ST8;   // bytes between the two buffers
+    constexpr unsigned MKBUF = 2u * ST4, SPBUF = (unsigned)Q * ST4;
     // island mode: this rank's window of the global zero-slot ranking / surplus list / slot numbering (uniform over the kernel)
     const long long zoff_mine = (ISLAND && decode) ? a.ctrl->zoff[a.isl.rank] : 0, eoff_mine = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank] : 0;
     const long long eoff_next = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank + 1] : 0, eoff_all = (ISLAND && decode) ? a.ctrl->eoff[a.isl.world] : 0;
     const uint32_t slot_lo = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;
-    uint32_t zfB = 0u, selfB = 0u;   // stage B result: bit h = slot h takes its surplus entry, bit 8+h = slot h takes particle 0
     // The look-ahead of the last iterations runs past the end of the population; it is clamped to the last group instead of
     // being branched around (the redundant copies are harmless), so that the loop body stays one basic block in which the
     // compiler can interleave the arithmetic of the thread's Q particles.
     const uint32_t glast = ngroups - 1u;
-    auto stageA = [&](uint32_t p) {
+    auto mask_word = [&](uint32_t p) { return (min(p, glast) * Q) >> 5; };
+    auto stageA = [&](uint32_t p, unsigned par) {
         if (ASYNC && decode) {
-            const uint32_t w = (min(p, glast) * Q) >> 5;
-            cp_async4(sa_mk, a.am.zmask + w);
-            cp_async4(sa_mk + ST4, a.am.zbase + w);
+            const uint32_t w = mask_word(p);
+            cp_async4(sa_mk + par * MKBUF, a.am.zmask + w);
+            cp_async4(sa_mk + par * MKBUF + ST4, a.am.zbase + w);
         }
     };
-    auto stageB = [&](uint32_t p) {   // consumes the bitmap word / rank base fetched for this p one iteration ago
-        if (ASYNC) {
-            const uint32_t s0 = Q * min(p, glast);
-            selfB = ISLAND ? slot_lo + s0 : s0;   // global slot id
-            zfB = 0u;
-            if (decode) {
-                const uint32_t mA = s_mk[0][tid], bA = s_mk[1][tid];
-                const uint32_t bit = s0 & 31u;
-                const uint32_t rank = bA + __popc(mA & ((1u << bit) - 1u));
-                const uint32_t zq = (mA >> bit) & ((1u << Q) - 1u);      // the group's zero-count flags
+    // Stage B proper: (bitmap word, rank base) of group p -> where each zero-count slot of the group finds its parent.
+    // `fetch(h, ptr)` receives the address of the surplus entry of slot h (local list, or a peer's list in island mode).
+    // Returns the flags readC needs: bit h = slot h takes the fetched entry, bit 8+h = slot h takes particle 0.
+    auto decodeB = [&](uint32_t p, uint32_t mA, uint32_t bA, auto&& fetch) -> uint32_t {
+        uint32_t zf = 0u;
+        const uint32_t s0 = Q * min(p, glast);
+        const uint32_t bit = s0 & 31u;
+        const uint32_t rank = bA + __popc(mA & ((1u << bit) - 1u));
+        const uint32_t zq = (mA >> bit) & ((1u << Q) - 1u);      // the group's zero-count flags
 #pragma unroll
-                for (int h = 0; h < Q; ++h) {
-                    if ((zq >> h) & 1u) {
-                        const uint32_t r = rank + __popc(zq & ((1u << h) - 1u));   // rank of this slot among the zero-count slots
-                        if (!ISLAND) {
-                            cp_async4(sa_sp + (unsigned)h * ST4, a.am.surplus + r);
-                            zfB |= 1u << h;
-                        } else {
-                            // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
-                            const long long m = zoff_mine + r;
-                            if (m >= eoff_mine && m < eoff_next) {   // the usual case: the entry is in this island's own list
-                                cp_async4(sa_sp + (unsigned)h * ST4, a.am.surplus + (m - eoff_mine));
-                                zfB |= 1u << h;
-                            } else if (m < eoff_all) {
-                                int o = 0;
-                                while (o + 1 < a.isl.world && m >= a.ctrl->eoff[o + 1]) ++o;
-                                const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.isl.base[o] + a.isl.off_surplus);
-                                cp_async4(sa_sp + (unsigned)h * ST4, sp + (m - a.ctrl->eoff[o]));
-                                zfB |= 1u << h;
-                            } else {
-                                zfB |= 0x100u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
-                            }
-                        }
+        for (int h = 0; h < Q; ++h) {
+            if ((zq >> h) & 1u) {
+                const uint32_t r = rank + __popc(zq & ((1u << h) - 1u));   // rank of this slot among the zero-count slots
+                if (!ISLAND) {
+                    fetch(h, a.am.surplus + r);
+                    zf |= 1u << h;
+                } else {
+                    // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
+                    const long long m = zoff_mine + r;
+                    if (m >= eoff_mine && m < eoff_next) {   // the usual case: the entry is in this island's own list
+                        fetch(h, a.am.surplus + (m - eoff_mine));
+                        zf |= 1u << h;
+                    } else if (m < eoff_all) {
+                        int o = 0;
+                        while (o + 1 < a.isl.world && m >= a.ctrl->eoff[o + 1]) ++o;
+                        const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.isl.base[o] + a.isl.off_surplus);
+                        fetch(h, sp + (m - a.ctrl->eoff[o]));
+                        zf |= 1u << h;
+                    } else {
+                        zf |= 0x100u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
                     }
                 }
             }
         }
+        return zf;
+    };
+    auto stageB = [&](uint32_t p, unsigned par) -> uint32_t {   // consumes the words stage A fetched into this parity's slots
+        if (ASYNC && decode) {
+            const unsigned base = sa_sp + par * SPBUF;
+            return decodeB(p, s_mk[par][0][tid], s_mk[par][1][tid], [&](int h, const uint32_t* g) { cp_async4(base + (unsigned)h * ST4, g); });
+        }
+        return 0u;
     };
     // stage C in two halves: the ancestors are read out of the thread's surplus slots BEFORE this iteration's stage B
     // overwrites them, the copies of the parents' state are issued AFTER stages A/B so that they form the younger of the
     // iteration's two cp.async groups (see the loop).
-    auto readC = [&](uint32_t (&anc)[Q]) {
+    auto readC = [&](uint32_t (&anc)[Q], uint32_t zf, uint32_t p, unsigned par) {
         if (ASYNC) {
+            const uint32_t self = slot_lo + Q * min(p, glast);   // global slot id of the group's first slot
 #pragma unroll
             for (int h = 0; h < Q; ++h)
-                anc[h] = ((zfB >> h) & 1u) ? s_sp[h][tid] : (((zfB >> (8 + h)) & 1u) ? 0u : selfB + h);
+                anc[h] = ((zf >> h) & 1u) ? s_sp[par][h][tid] : (((zf >> (8 + h)) & 1u) ? 0u : self + h);
         }
     };
     auto issueC = [&](const uint32_t (&anc)[Q], uint32_t p, unsigned buf) {
@@ -286,19 +297,44 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
         }
     };
-    // Pipeline: iteration i works on group G_i = p0 + i S and issues, in this order,
-    //   group "AB":  stage B for G_{i+3} (rank -> surplus entries), stage A for G_{i+4} (bitmap word + rank base)
-    //   group "C":   the parents' state for G_{i+2}, into the buffer iteration i has just emptied
-    // cp.async groups complete in order, so "all but the youngest group" at the top of an iteration means: the state gathered
-    // TWO iterations ago and the small stage A/B copies of the last iteration have landed, while the last iteration's state
-    // gather may still be in flight.
+    // Pipeline: iteration i (parity par = i & 1) works on group G_i = p0 + i S and issues, in this order,
+    //   group "AB":  stage B for G_{i+4} (rank -> surplus entries, from the words stage A fetched in iteration i-2),
+    //                stage A for G_{i+6} (bitmap word + rank base)
+    //   group "C":   the parents' state for G_{i+2} (ancestors from the entries stage B fetched in iteration i-2), into the
+    //                buffer iteration i has just emptied
+    // cp.async groups complete in order, so "all but the two youngest groups" at the top of an iteration means: everything
+    // issued two or more iterations ago has landed, while the last iteration's copies may still be in flight.
+    uint32_t zf_old = 0u, zf_new = 0u;   // stage B flags of G_{i+2} and G_{i+3} at the top of iteration i
     if (ASYNC) {
-        uint32_t anc[Q];
-        stageA(p0); cp_async_commit(); cp_async_wait_all();
-        stageB(p0); stageA(p0 + stride); cp_async_commit(); cp_async_wait_all();
-        readC(anc); stageB(p0 + stride); stageA(p0 + 2 * stride); issueC(anc, p0, 0u); cp_async_commit(); cp_async_wait_all();
-        readC(anc); stageB(p0 + 2 * stride); stageA(p0 + 3 * stride); cp_async_commit();
-        issueC(anc, p0 + stride, 1u); cp_async_commit();
+        // Prologue: the links of the first groups are chased with plain loads, batched so that only two memory latencies are
+        // exposed (bitmap words of G_0..G_5 together, then the surplus entries of G_0..G_3 together).
+        uint32_t anc0[Q], anc1[Q];
+        if (decode) {
+            uint32_t mA[6], bA[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { const uint32_t w = mask_word(p0 + (uint32_t)k * stride); mA[k] = __ldg(a.am.zmask + w); bA[k] = __ldg(a.am.zbase + w); }
+            s_mk[0][0][tid] = mA[4]; s_mk[0][1][tid] = bA[4];
+            s_mk[1][0][tid] = mA[5]; s_mk[1][1][tid] = bA[5];
+            uint32_t e0[Q], e1[Q];
+#pragma unroll
+            for (int h = 0; h < Q; ++h) { e0[h] = 0u; e1[h] = 0u; }
+            const uint32_t zf0 = decodeB(p0, mA[0], bA[0], [&](int h, const uint32_t* g) { e0[h] = *g; });
+            const uint32_t zf1 = decodeB(p0 + stride, mA[1], bA[1], [&](int h, const uint32_t* g) { e1[h] = *g; });
+            zf_old = decodeB(p0 + 2 * stride, mA[2], bA[2], [&](int h, const uint32_t* g) { cp_async4(sa_sp + (unsigned)h * ST4, g); });
+            zf_new = decodeB(p0 + 3 * stride, mA[3], bA[3], [&](int h, const uint32_t* g) { cp_async4(sa_sp + SPBUF + (unsigned)h * ST4, g); });
+            const uint32_t self0 = slot_lo + Q * min(p0, glast), self1 = slot_lo + Q * min(p0 + stride, glast);
+#pragma unroll
+            for (int h = 0; h < Q; ++h) {
+                anc0[h] = ((zf0 >> h) & 1u) ? e0[h] : (((zf0 >> (8 + h)) & 1u) ? 0u : self0 + h);
+                anc1[h] = ((zf1 >> h) & 1u) ? e1[h] : (((zf1 >> (8 + h)) & 1u) ? 0u : self1 + h);
+            }
+        } else {
+            readC(anc0, 0u, p0, 0u);
+            readC(anc1, 0u, p0 + stride, 0u);
+        }
+        issueC(anc0, p0, 0u); cp_async_commit();            // together with the surplus entries of G_2 / G_3
+        issueC(anc1, p0 + stride, 1u); cp_async_commit();
+        cp_async_commit();                                   // empty group: iteration 0 waits for all but the two youngest
     }
     unsigned buf = 0u;
 
@@ -310,7 +346,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         for (int h = 0; h < Q; ++h) has[h] = FULL || s0 + h < n32;
         double x[Q][D], lwv[Q];
         if (PHASE != PHASE_INIT) {
-            if (ASYNC) cp_async_wait_but_youngest();
+            if (ASYNC) cp_async_wait_but_two();
 #pragma unroll
             for (int h = 0; h < Q; ++h) {
 #pragma unroll
@@ -321,12 +357,13 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             // advance the pipeline before the arithmetic of this group
             if (ASYNC) {
                 uint32_t anc[Q];
-                readC(anc);
-                stageB(p + 3 * stride);
-                stageA(p + 4 * stride);
+                readC(anc, zf_old, p + 2 * stride, buf);
+                const uint32_t zf_cur = stageB(p + 4 * stride, buf);
+                stageA(p + 6 * stride, buf);
                 cp_async_commit();
                 issueC(anc, p + 2 * stride, buf);
                 cp_async_commit();
+                zf_old = zf_new; zf_new = zf_cur;
                 buf ^= 1u;
             }
             if (NOBS > 0) {  // moments of the population as the reference's Integrate sees it (sampler.h:559-571)
@@ -749,10 +786,9 @@ public:
             SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
         }
         StepArgs<Model> a = args();
-        if (island()) { no_inject(); k_step<Model, PHASE_INIT, false, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a); }
-        else if (znoise_) k_step<Model, PHASE_INIT, true><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
-        else k_step<Model, PHASE_INIT, false><<<grid_init_, STEP_THREADS, 0, stream_>>>(a);
-        SMCB_CUDA(cudaGetLastError());
+        if (island()) { no_inject(); launch_chained(k_step<Model, PHASE_INIT, false, true>, grid_init_, STEP_THREADS, stream_, a); }
+        else if (znoise_) launch_chained(k_step<Model, PHASE_INIT, true, false>, grid_init_, STEP_THREADS, stream_, a);
+        else launch_chained(k_step<Model, PHASE_INIT, false, false>, grid_init_, STEP_THREADS, stream_, a);
         if (after_launch_) after_launch_();
         enqueue_resample();
         steps_ = 1;
@@ -760,10 +796,9 @@ public:
     // sampler.h:701-764
     void Iterate() {
         StepArgs<Model> a = args();
-        if (island()) k_step<Model, PHASE_MOVE, false, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
-        else if (znoise_) k_step<Model, PHASE_MOVE, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
-        else k_step<Model, PHASE_MOVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
-        SMCB_CUDA(cudaGetLastError());
+        if (island()) launch_chained(k_step<Model, PHASE_MOVE, false, true>, grid_move_, STEP_THREADS, stream_, a);
+        else if (znoise_) launch_chained(k_step<Model, PHASE_MOVE, true, false>, grid_move_, STEP_THREADS, stream_, a);
+        else launch_chained(k_step<Model, PHASE_MOVE, false, false>, grid_move_, STEP_THREADS, stream_, a);
         if (after_launch_) after_launch_();
         enqueue_resample();
         ++steps_;
@@ -823,9 +858,8 @@ public:
     // Fused Integrate for the current (last) population: closes the observable trace.
     void ObserveFinal() {
         StepArgs<Model> a = args();
-        if (island()) k_step<Model, PHASE_OBSERVE, false, true><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
-        else k_step<Model, PHASE_OBSERVE, false><<<grid_move_, STEP_THREADS, 0, stream_>>>(a);
-        SMCB_CUDA(cudaGetLastError());
+        if (island()) launch_chained(k_step<Model, PHASE_OBSERVE, false, true>, grid_move_, STEP_THREADS, stream_, a);
+        else launch_chained(k_step<Model, PHASE_OBSERVE, false, false>, grid_move_, STEP_THREADS, stream_, a);
         if (after_launch_) after_launch_();
     }
     // Called after every kernel launch (per-kernel event timing in the benchmark).

@@ -666,6 +666,9 @@ __device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t (&v)[8]
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
+#ifndef SMCB_RS_MASS_DESC
+#define SMCB_RS_MASS_DESC 1
+#endif
 enum { SRC_WTILDE = 2 };   // weights exp(lw - c) against a step-wide shift c, normalised by one multiplication (k_step writes them)
 
 struct RsView {            // how the three passes see the workspace of ScanArgs
@@ -698,6 +701,8 @@ __device__ __forceinline__ void rs_chunk(int ntiles, int& t0, int& t1) {
 
 template <int SRC, bool ISLAND>
 __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
+    pdl_wait_for_predecessor();
+    pdl_release_successor();
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     const int lane = threadIdx.x & 31;
     const int n32 = (int)a.n;
@@ -706,7 +711,11 @@ __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
     const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
     const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;   // SRC_WTILDE: lse_ptr points at 1 / sum of the shifted weights
     const int nw = (int)(gridDim.x * (RP_THREADS / 32));
-    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
+    // Tiles are taken from the END of the array downwards: k_step has just written the weights in ascending order, so the
+    // top of the array is what the L2 still holds (the array as a whole, 134 MB at 2^24, does not fit), and this pass in turn
+    // leaves the bottom of the array most recently used for the count pass that follows.
+    for (int rt = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); rt < ntiles; rt += nw) {
+        const int tile = SMCB_RS_MASS_DESC ? ntiles - 1 - rt : rt;
         const int base = tile * RP_TILE;
         double s = 0.0;
         if (base + RP_TILE <= n32) {   // coalesced 16-byte loads; the order inside a tile does not matter for an exact sum
@@ -854,6 +863,8 @@ __device__ __forceinline__ void rs_count_body(const ScanArgs& a) {
 #endif
 template <int SRC, int MODE, bool ISLAND>
 __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_COUNT_MINB) k_rs_count(ScanArgs a) {
+    pdl_wait_for_predecessor();
+    pdl_release_successor();
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     const long long nthr = ISLAND ? a.n_glob : a.n;
     if ((nthr & (nthr - 1)) == 0) rs_count_body<SRC, MODE, ISLAND, true>(a);
@@ -863,6 +874,8 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_COUNT_MINB) k_rs_count(Sca
 constexpr int RP_WINDOW = 512;                  // surplus entries expanded per shared-memory window (per warp)
 template <bool ISLAND>
 __global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
+    pdl_wait_for_predecessor();
+    pdl_release_successor();
     if (a.enable_ptr && *a.enable_ptr == 0) return;
     __shared__ uint32_t s_seg[RP_THREADS / 32][RP_WINDOW];
     const int lane = threadIdx.x & 31;
@@ -1036,12 +1049,11 @@ inline size_t resample_cslot_entries(long long n) { return (size_t)((n + RP_TILE
 template <int SRC, int MODE, bool ISLAND = false>
 inline void launch_resample_passes(const ScanArgs& a, cudaStream_t stream, const std::function<void()>* after = nullptr) {
     const int grid = resample_pass_grid(a.n);
-    k_rs_mass<SRC, ISLAND><<<resample_pass_grid(a.n, 8), RP_THREADS, 0, stream>>>(a);   // pure streaming: more warps in flight
+    launch_chained(k_rs_mass<SRC, ISLAND>, resample_pass_grid(a.n, 8), RP_THREADS, stream, a);   // pure streaming: more warps in flight
     if (after && *after) (*after)();
-    k_rs_count<SRC, MODE, ISLAND><<<grid, RP_THREADS, 0, stream>>>(a);
+    launch_chained(k_rs_count<SRC, MODE, ISLAND>, grid, RP_THREADS, stream, a);
     if (after && *after) (*after)();
-    k_rs_map<ISLAND><<<grid, RP_THREADS, 0, stream>>>(a);
-    SMCB_CUDA(cudaGetLastError());
+    launch_chained(k_rs_map<ISLAND>, grid, RP_THREADS, stream, a);
 }
 
 // ---- island mode: integer weight mass of this rank, all-gathered so that every rank knows where its scan starts --------
