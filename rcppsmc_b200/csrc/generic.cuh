@@ -23,6 +23,7 @@
 // IterateBack (sampler.h:684-699), the history getters (:153-177), ancestral lines (:445-476) and the path-sampling
 // integrals (:602-669) on top.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -452,7 +453,7 @@ public:
     // ---- state getters (sampler.h:145-197)
     long GetNumber() const { return n_; }
     long GetTime() const { return T_; }
-    double GetESS() { Population<Model> pop(this); double e; (void)pop_lse(IdentityLogW{}, &e); return e; }
+    double GetESS() { double e; (void)pop_lse(IdentityLogW{}, &e); return e; }
     double GetESS(long gen) const { return history_.at(gen).ess; }
     int GetAccepted() const { return n_accepted_; }
     int GetResampled() const { return n_resampled_; }
@@ -545,8 +546,7 @@ public:
 
     void Sync() { SMCB_CUDA(cudaStreamSynchronize(stream_)); }
 
-private:
-    friend class Population<Model>;
+    // (functor types that reach a kernel template must be public: nvcc restriction)
     struct IdentityLogW { __device__ double operator()(const double (&)[D], double lw) const { return lw; } };
     template <class F> struct IntegrateOp {
         F f;
@@ -560,6 +560,8 @@ private:
         }
     };
 
+private:
+    friend class Population<Model>;
     PopView<D> view() const {
         PopView<D> v;
         double* const* cur = parity_ ? xb_ : xa_;

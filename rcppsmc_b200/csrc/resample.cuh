@@ -666,9 +666,6 @@ __device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t (&v)[8]
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
-#ifndef SMCB_RS_MASS_DESC
-#define SMCB_RS_MASS_DESC 1
-#endif
 enum { SRC_WTILDE = 2 };   // weights exp(lw - c) against a step-wide shift c, normalised by one multiplication (k_step writes them)
 
 struct RsView {            // how the three passes see the workspace of ScanArgs
@@ -711,11 +708,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
     const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
     const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;   // SRC_WTILDE: lse_ptr points at 1 / sum of the shifted weights
     const int nw = (int)(gridDim.x * (RP_THREADS / 32));
-    // Tiles are taken from the END of the array downwards: k_step has just written the weights in ascending order, so the
-    // top of the array is what the L2 still holds (the array as a whole, 134 MB at 2^24, does not fit), and this pass in turn
-    // leaves the bottom of the array most recently used for the count pass that follows.
-    for (int rt = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); rt < ntiles; rt += nw) {
-        const int tile = SMCB_RS_MASS_DESC ? ntiles - 1 - rt : rt;
+    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
         const int base = tile * RP_TILE;
         double s = 0.0;
         if (base + RP_TILE <= n32) {   // coalesced 16-byte loads; the order inside a tile does not matter for an exact sum
@@ -872,8 +865,11 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_COUNT_MINB) k_rs_count(Sca
 }
 
 constexpr int RP_WINDOW = 512;                  // surplus entries expanded per shared-memory window (per warp)
+#ifndef SMCB_RS_MAP_MINB
+#define SMCB_RS_MAP_MINB 4
+#endif
 template <bool ISLAND>
-__global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
+__global__ void __launch_bounds__(RP_THREADS, SMCB_RS_MAP_MINB) k_rs_map(ScanArgs a) {
     pdl_wait_for_predecessor();
     pdl_release_successor();
     if (a.enable_ptr && *a.enable_ptr == 0) return;
@@ -884,7 +880,6 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
     const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
     const RsView V = rs_view(a, ntiles);
     const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
-    const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
     int t0, t1;
     rs_chunk(ntiles, t0, t1);
@@ -901,16 +896,15 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rs_map(ScanArgs a) {
             Z = (int)acc;
         }
         int clast = t0 > 0 ? (int)a.cslot[t0 * RP_TILE - 1] : 0;    // c of the slot in front of the tile
+        uint32_t unext[8];
+        ld_global_v8(a.cslot + t0 * RP_TILE + lane * RP_ITEMS, unext);
         for (int tile = t0; tile < t1; ++tile) {
             const int g0 = tile * RP_TILE + lane * RP_ITEMS;
             const int nv = min(max(n32 - g0, 0), RP_ITEMS);
             int c[RP_ITEMS];
-            {
-                uint32_t u[8];
-                ld_global_v8(a.cslot + g0, u);
 #pragma unroll
-                for (int k = 0; k < RP_ITEMS; ++k) c[k] = (int)u[k];
-            }
+            for (int k = 0; k < RP_ITEMS; ++k) c[k] = (int)unext[k];
+            if (tile + 1 < t1) ld_global_v8(a.cslot + g0 + RP_TILE, unext);   // the next tile's counts are in flight during the work below
             int cfirst = __shfl_up_sync(SMCB_FULL, c[RP_ITEMS - 1], 1);
             if (lane == 0) cfirst = clast;
             clast = __shfl_sync(SMCB_FULL, c[RP_ITEMS - 1], 31);
@@ -1053,7 +1047,7 @@ inline void launch_resample_passes(const ScanArgs& a, cudaStream_t stream, const
     if (after && *after) (*after)();
     launch_chained(k_rs_count<SRC, MODE, ISLAND>, grid, RP_THREADS, stream, a);
     if (after && *after) (*after)();
-    launch_chained(k_rs_map<ISLAND>, grid, RP_THREADS, stream, a);
+    launch_chained(k_rs_map<ISLAND>, resample_pass_grid(a.n, SMCB_RS_MAP_MINB), RP_THREADS, stream, a);
 }
 
 // ---- island mode: integer weight mass of this rank, all-gathered so that every rank knows where its scan starts --------
