@@ -67,8 +67,8 @@ struct Ctrl {
     unsigned long long floor_total;  // RESIDUAL: deterministic children handed out this step
     // island mode (one rank of a partitioned population)
     unsigned long long mass_offset;  // integer weight mass of all lower ranks (start of this rank's cumulative scan)
-    long long zoff[ISL_MAX + 2];     // zero-count slots before each rank (exclusive prefix; [world] = total; [ISL_MAX+1] = this rank's own)
-    long long eoff[ISL_MAX + 2];     // surplus-list entries before each rank (same layout)
+    long long zoff[ISL_MAX + 2];     // [ISL_MAX+1]: this rank's zero-count slots of the current pass (stash between two blocks of k_rs_map)
+    long long eoff[ISL_MAX + 2];     // [ISL_MAX+1]: this rank's surplus-list entries, likewise
     // what may change between two filters of the same shape (so that a captured CUDA graph of the filter can be replayed):
     unsigned long long seed;         // Philox key of this run
     double mparam[4];                // model parameters picked up by Model::load_dynamic (e.g. the PMMH proposal)
@@ -121,6 +121,43 @@ __device__ __forceinline__ void st_global_v4(double* p, double a, double b, doub
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_two() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+
+// Island mode, cold paths of the ancestor decode (groups of slots near the island boundaries).  Surplus lists hold LOCAL parent
+// ids of the island that owns the list; `bases` is the table of slab addresses (shared-memory copy of IslandInfo::base), `eoff`
+// the exclusive prefix of the ranks' list lengths.
+// Where does the zero-count slot of global rank m find its entry?  Returns the address (own list or a peer's, over NVLink) and
+// the owning rank, or nullptr beyond all lists (the slot takes particle 0, sampler.h:845).
+static __device__ __forceinline__ const uint32_t* isl_entry(const uint32_t* eoff, unsigned char* const* bases, size_t off_surplus, int world, uint32_t m, int& owner) {
+    owner = 0;
+    if (m >= eoff[world]) return nullptr;
+    int o = 0;
+    while (o + 1 < world && m >= eoff[o + 1]) ++o;
+    owner = o;
+    return reinterpret_cast<const uint32_t*>(bases[o] + off_surplus) + (m - eoff[o]);
+}
+// Flags of slot h (see decodeB) for an entry owned by `owner` (nullptr: particle 0, which lives on rank 0).
+__device__ __forceinline__ uint32_t isl_flags(int h, bool have_entry, int owner, int my_rank) {
+    const uint32_t far = owner != my_rank ? ((0x10000u << h) | ((uint32_t)owner << (20 + 3 * h))) : 0u;
+    return (have_entry ? (1u << h) : (0x100u << h)) | far;
+}
+// One whole group (up to 4 slots) through the cold path, entries copied into the thread's shared-memory slots (`smem_dst` =
+// slot 0, slot h sits h * 4 * STEP_THREADS bytes further).  zq = zero-count flags of the group, m0 = global zero-slot rank of
+// its first zero-count slot.
+static __device__ __noinline__ uint32_t isl_cold_group(uint32_t zq, uint32_t m0, unsigned smem_dst, const uint32_t* eoff,
+                                                       unsigned char* const* bases, size_t off_surplus, int world, int my_rank) {
+    uint32_t zf = 0u;
+    for (int h = 0; h < 4; ++h) {
+        if (!((zq >> h) & 1u)) continue;
+        int o;
+        const uint32_t* g = isl_entry(eoff, bases, off_surplus, world, m0 + __popc(zq & ((1u << h) - 1u)), o);
+        if (g) cp_async4(smem_dst + (unsigned)h * (STEP_THREADS * 4u), g);
+        zf |= isl_flags(h, g != nullptr, o, my_rank);
+    }
+    return zf;
+}
+static __device__ __noinline__ const double* isl_far_state(unsigned char* const* bases, size_t off_x, int owner, uint32_t local) {
+    return reinterpret_cast<const double*>(bases[owner] + off_x) + local;
+}
 
 template <class Model, int PHASE, bool INJECT, bool ISLAND = false>
 __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<Model> a) {
@@ -185,6 +222,12 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     __shared__ uint32_t s_sp[2][Q][ASYNC ? STEP_THREADS : 1];   // [iteration parity] surplus entries of the group
     __shared__ double s_x[2][Q][D][ASYNC ? STEP_THREADS : 1];   // parents' state, double-buffered (gathered two iterations ahead)
     __shared__ double s_lw[2][Q][ASYNC ? STEP_THREADS : 1];     // stored log-weights (no resampling last step), likewise
+    __shared__ unsigned char* s_isl_base[ISLAND ? ISL_MAX : 1];  // island mode: every rank's slab (table for the cold decode paths)
+    __shared__ uint32_t s_zoff[ISLAND ? ISL_MAX + 1 : 1], s_eoff[ISLAND ? ISL_MAX + 1 : 1];   // zero slots / surplus entries before each rank
+    if (ISLAND) {
+        if (tid < ISL_MAX) s_isl_base[tid] = a.isl.base[tid];
+        __syncthreads();
+    }
     // The loop exists in two versions, selected by one uniform branch: after a resampling step (ancestor decode, uniform
     // weights) and after a step that kept its population (own slot, stored log-weights).  Inside each, the last, ragged
     // group of a population whose size is not a multiple of Q runs through a second copy of the body (FULL = false), so
@@ -198,10 +241,28 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     constexpr unsigned ST4 = STEP_THREADS * 4u, ST8 = STEP_THREADS * 8u;
     constexpr unsigned XBUF = (unsigned)(Q * D) * ST8, LBUF = (unsigned)Q * ST8;   // bytes between the two buffers
     constexpr unsigned MKBUF = 2u * ST4, SPBUF = (unsigned)Q * ST4;
-    // island mode: this rank's window of the global zero-slot ranking / surplus list / slot numbering (uniform over the kernel)
-    const long long zoff_mine = (ISLAND && decode) ? a.ctrl->zoff[a.isl.rank] : 0, eoff_mine = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank] : 0;
-    const long long eoff_next = (ISLAND && decode) ? a.ctrl->eoff[a.isl.rank + 1] : 0, eoff_all = (ISLAND && decode) ? a.ctrl->eoff[a.isl.world] : 0;
-    const uint32_t slot_lo = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;
+    // island mode: this rank's window of the global zero-slot ranking / surplus list / slot numbering (uniform over the kernel;
+    // the whole population has fewer than 2^31 slots, so 32-bit arithmetic)
+    if (ISLAND && decode) {
+        // every rank's (zero-count slots, surplus entries) of the resampling pass that has just finished: posted by the first
+        // block of each rank's k_step into every mailbox, picked up here by every block.  Their arrival is also the signal that
+        // the peers' surplus lists and parent states may be read over NVLink (hence the fence before anyone does).
+        if (warp == 0) {
+            const unsigned long long seq = (a.isl.epoch << 24) + (unsigned long long)T + 1ull;
+            if (blockIdx.x == 0) {   // this rank's own totals (left in the control block by its map pass) go out to every rank
+                double mine[2] = {(double)a.ctrl->zoff[ISL_MAX + 1], (double)a.ctrl->eoff[ISL_MAX + 1]};
+                __threadfence_system();
+                island_send(a.isl, ISL_KIND_ZE, seq, mine, 2);
+            }
+            island_ze_offsets(a.isl, seq, s_zoff, s_eoff);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const uint32_t zoff_mine = (ISLAND && decode) ? s_zoff[a.isl.rank] : 0u;
+    const uint32_t zrel = (ISLAND && decode) ? zoff_mine - s_eoff[a.isl.rank] : 0u;   // local zero-slot rank -> position in the own surplus list
+    const uint32_t elen_mine = (ISLAND && decode) ? s_eoff[a.isl.rank + 1] - s_eoff[a.isl.rank] : 0u;
+    const uint32_t* const own_list = a.am.surplus + (int32_t)zrel;   // indexed by the local zero-slot rank
     // The look-ahead of the last iterations runs past the end of the population; it is clamped to the last group instead of
     // being branched around (the redundant copies are harmless), so that the loop body stays one basic block in which the
     // compiler can interleave the arithmetic of the thread's Q particles.
@@ -215,85 +276,71 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         }
     };
     // Stage B proper: (bitmap word, rank base) of group p -> where each zero-count slot of the group finds its parent.
-    // `fetch(h, ptr)` receives the address of the surplus entry of slot h (local list, or a peer's list in island mode).
-    // Returns the flags readC needs: bit h = slot h takes the fetched entry, bit 8+h = slot h takes particle 0.
-    auto decodeB = [&](uint32_t p, uint32_t mA, uint32_t bA, auto&& fetch) -> uint32_t {
-        uint32_t zf = 0u;
+    // `fetch(h, ptr)` receives the address of the surplus entry of slot h in this rank's own list.  Returns the flags readC and
+    // issueC need: bit h = slot h takes the fetched entry, bit 8+h = slot h takes particle 0; island mode only: bit 16+h = the
+    // parent of slot h lives on another island, whose rank is in bits 20+3h .. 22+3h.
+    // Island mode: a surplus list holds LOCAL parent ids, and a group whose zero-count slots all find their entries in this
+    // island's OWN list -- every group except a few near the island boundaries -- runs exactly the single-GPU code (the list
+    // pointer is pre-shifted by the offset between the local zero-slot ranking and the list).  ONE range check per group sends
+    // the others through `cold(zq, m0)`.
+    auto decodeB = [&](uint32_t p, uint32_t mA, uint32_t bA, auto&& fetch, auto&& cold) -> uint32_t {
         const uint32_t s0 = Q * min(p, glast);
         const uint32_t bit = s0 & 31u;
         const uint32_t rank = bA + __popc(mA & ((1u << bit) - 1u));
         const uint32_t zq = (mA >> bit) & ((1u << Q) - 1u);      // the group's zero-count flags
+        if (ISLAND) {
+            const uint32_t lo = rank + zrel;                      // wraps to a huge value in front of the own list
+            if (!(lo <= elen_mine && lo + (uint32_t)__popc(zq) <= elen_mine)) return cold(zq, zoff_mine + rank);
+        }
 #pragma unroll
         for (int h = 0; h < Q; ++h) {
-            if ((zq >> h) & 1u) {
-                const uint32_t r = rank + __popc(zq & ((1u << h) - 1u));   // rank of this slot among the zero-count slots
-                if (!ISLAND) {
-                    fetch(h, a.am.surplus + r);
-                    zf |= 1u << h;
-                } else {
-                    // global zero-slot rank -> the island whose surplus list holds it -> (possibly remote) entry
-                    const long long m = zoff_mine + r;
-                    if (m >= eoff_mine && m < eoff_next) {   // the usual case: the entry is in this island's own list
-                        fetch(h, a.am.surplus + (m - eoff_mine));
-                        zf |= 1u << h;
-                    } else if (m < eoff_all) {
-                        int o = 0;
-                        while (o + 1 < a.isl.world && m >= a.ctrl->eoff[o + 1]) ++o;
-                        const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.isl.base[o] + a.isl.off_surplus);
-                        fetch(h, sp + (m - a.ctrl->eoff[o]));
-                        zf |= 1u << h;
-                    } else {
-                        zf |= 0x100u << h;   // beyond the available surplus children: particle 0 (sampler.h:845)
-                    }
-                }
-            }
+            const uint32_t r = rank + __popc(zq & ((1u << h) - 1u));   // rank of this slot among the zero-count slots
+            if ((zq >> h) & 1u) fetch(h, own_list + r);
         }
-        return zf;
+        return zq;
     };
     auto stageB = [&](uint32_t p, unsigned par) -> uint32_t {   // consumes the words stage A fetched into this parity's slots
         if (ASYNC && decode) {
             const unsigned base = sa_sp + par * SPBUF;
-            return decodeB(p, s_mk[par][0][tid], s_mk[par][1][tid], [&](int h, const uint32_t* g) { cp_async4(base + (unsigned)h * ST4, g); });
+            return decodeB(p, s_mk[par][0][tid], s_mk[par][1][tid], [&](int h, const uint32_t* g) { cp_async4(base + (unsigned)h * ST4, g); },
+                           [&](uint32_t zq, uint32_t m0) { return isl_cold_group(zq, m0, base, s_eoff, s_isl_base, a.isl.off_surplus, a.isl.world, a.isl.rank); });
         }
         return 0u;
     };
     // stage C in two halves: the ancestors are read out of the thread's surplus slots BEFORE this iteration's stage B
     // overwrites them, the copies of the parents' state are issued AFTER stages A/B so that they form the younger of the
-    // iteration's two cp.async groups (see the loop).
+    // iteration's two cp.async groups (see the loop).  anc[h] = local index of the parent on the island that owns it.
+    auto resolve = [&](uint32_t zf, int h, uint32_t entry, uint32_t self_local) -> uint32_t {
+        return ((zf >> h) & 1u) ? entry : (((zf >> (8 + h)) & 1u) ? 0u : self_local + (uint32_t)h);
+    };
     auto readC = [&](uint32_t (&anc)[Q], uint32_t zf, uint32_t p, unsigned par) {
         if (ASYNC) {
-            const uint32_t self = slot_lo + Q * min(p, glast);   // global slot id of the group's first slot
+            const uint32_t self = Q * min(p, glast);
 #pragma unroll
-            for (int h = 0; h < Q; ++h)
-                anc[h] = ((zf >> h) & 1u) ? s_sp[par][h][tid] : (((zf >> (8 + h)) & 1u) ? 0u : self + h);
+            for (int h = 0; h < Q; ++h) anc[h] = resolve(zf, h, s_sp[par][h][tid], self);
         }
     };
-    auto issueC = [&](const uint32_t (&anc)[Q], uint32_t p, unsigned buf) {
+    auto issueC = [&](const uint32_t (&anc)[Q], uint32_t zf, uint32_t p, unsigned buf) {
         if (ASYNC) {
             const uint32_t s0 = Q * min(p, glast);
             const unsigned bx = sa_x + buf * XBUF, bl = sa_lw + buf * LBUF;
+            if (ISLAND && (zf >> 16)) {   // cold: some parent of this group is copied from its owner's slab over NVLink
+#pragma unroll 1
+                for (int h = 0; h < Q; ++h) {
+                    const int owner = ((zf >> (16 + h)) & 1u) ? (int)((zf >> (20 + 3 * h)) & 7u) : a.isl.rank;
 #pragma unroll
-            for (int h = 0; h < Q; ++h) {   // slots past the end of a ragged last group read the arrays' alignment padding (never used)
-                if (!ISLAND) {
+                    for (int d = 0; d < D; ++d)
+                        cp_async8(bx + (unsigned)(h * D + d) * ST8, isl_far_state(s_isl_base, parity ? a.isl.off_xb[d] : a.isl.off_xa[d], owner, anc[h]));
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < Q; ++h)   // slots past the end of a ragged last group read the arrays' alignment padding (never used)
 #pragma unroll
                     for (int d = 0; d < D; ++d) cp_async8(bx + (unsigned)(h * D + d) * ST8, src[d] + anc[h]);
-                } else {
-                    // the parent may live on another island: copy it from the owner's slab over NVLink
-                    const uint32_t rel = anc[h] - slot_lo;
-                    if (rel < (uint32_t)a.isl.n_loc) {   // the usual case under systematic / stratified resampling: a local parent
+            }
+            if (!RES) {
 #pragma unroll
-                        for (int d = 0; d < D; ++d) cp_async8(bx + (unsigned)(h * D + d) * ST8, src[d] + rel);
-                    } else {
-                        const int o = (int)(anc[h] / (uint32_t)a.isl.n_loc);
-                        const long long li = (long long)anc[h] - (long long)o * a.isl.n_loc;
-#pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            const double* xs = reinterpret_cast<const double*>(a.isl.base[o] + (parity ? a.isl.off_xb[d] : a.isl.off_xa[d]));
-                            cp_async8(bx + (unsigned)(h * D + d) * ST8, xs + li);
-                        }
-                    }
-                }
-                if (!RES) cp_async8(bl + (unsigned)h * ST8, a.lw + s0 + h);
+                for (int h = 0; h < Q; ++h) cp_async8(bl + (unsigned)h * ST8, a.lw + s0 + h);
             }
         }
     };
@@ -308,7 +355,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     if (ASYNC) {
         // Prologue: the links of the first groups are chased with plain loads, batched so that only two memory latencies are
         // exposed (bitmap words of G_0..G_5 together, then the surplus entries of G_0..G_3 together).
-        uint32_t anc0[Q], anc1[Q];
+        uint32_t anc0[Q], anc1[Q], zf0 = 0u, zf1 = 0u;
         if (decode) {
             uint32_t mA[6], bA[6];
 #pragma unroll
@@ -318,22 +365,37 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             uint32_t e0[Q], e1[Q];
 #pragma unroll
             for (int h = 0; h < Q; ++h) { e0[h] = 0u; e1[h] = 0u; }
-            const uint32_t zf0 = decodeB(p0, mA[0], bA[0], [&](int h, const uint32_t* g) { e0[h] = *g; });
-            const uint32_t zf1 = decodeB(p0 + stride, mA[1], bA[1], [&](int h, const uint32_t* g) { e1[h] = *g; });
-            zf_old = decodeB(p0 + 2 * stride, mA[2], bA[2], [&](int h, const uint32_t* g) { cp_async4(sa_sp + (unsigned)h * ST4, g); });
-            zf_new = decodeB(p0 + 3 * stride, mA[3], bA[3], [&](int h, const uint32_t* g) { cp_async4(sa_sp + SPBUF + (unsigned)h * ST4, g); });
-            const uint32_t self0 = slot_lo + Q * min(p0, glast), self1 = slot_lo + Q * min(p0 + stride, glast);
+            // cold handlers: the first two groups take their entries into registers, the next two into the shared-memory slots
+            auto cold_reg = [&](uint32_t (&e)[Q]) {
+                return [&](uint32_t zq, uint32_t m0) {
+                    uint32_t zf = 0u;
 #pragma unroll
-            for (int h = 0; h < Q; ++h) {
-                anc0[h] = ((zf0 >> h) & 1u) ? e0[h] : (((zf0 >> (8 + h)) & 1u) ? 0u : self0 + h);
-                anc1[h] = ((zf1 >> h) & 1u) ? e1[h] : (((zf1 >> (8 + h)) & 1u) ? 0u : self1 + h);
-            }
+                    for (int h = 0; h < Q; ++h) {
+                        if (!((zq >> h) & 1u)) continue;
+                        int o;
+                        const uint32_t* g = isl_entry(s_eoff, s_isl_base, a.isl.off_surplus, a.isl.world, m0 + __popc(zq & ((1u << h) - 1u)), o);
+                        if (g) e[h] = *g;
+                        zf |= isl_flags(h, g != nullptr, o, a.isl.rank);
+                    }
+                    return zf;
+                };
+            };
+            auto cold_smem = [&](unsigned base) {
+                return [&, base](uint32_t zq, uint32_t m0) { return isl_cold_group(zq, m0, base, s_eoff, s_isl_base, a.isl.off_surplus, a.isl.world, a.isl.rank); };
+            };
+            zf0 = decodeB(p0, mA[0], bA[0], [&](int h, const uint32_t* g) { e0[h] = *g; }, cold_reg(e0));
+            zf1 = decodeB(p0 + stride, mA[1], bA[1], [&](int h, const uint32_t* g) { e1[h] = *g; }, cold_reg(e1));
+            zf_old = decodeB(p0 + 2 * stride, mA[2], bA[2], [&](int h, const uint32_t* g) { cp_async4(sa_sp + (unsigned)h * ST4, g); }, cold_smem(sa_sp));
+            zf_new = decodeB(p0 + 3 * stride, mA[3], bA[3], [&](int h, const uint32_t* g) { cp_async4(sa_sp + SPBUF + (unsigned)h * ST4, g); }, cold_smem(sa_sp + SPBUF));
+            const uint32_t self0 = Q * min(p0, glast), self1 = Q * min(p0 + stride, glast);
+#pragma unroll
+            for (int h = 0; h < Q; ++h) { anc0[h] = resolve(zf0, h, e0[h], self0); anc1[h] = resolve(zf1, h, e1[h], self1); }
         } else {
             readC(anc0, 0u, p0, 0u);
             readC(anc1, 0u, p0 + stride, 0u);
         }
-        issueC(anc0, p0, 0u); cp_async_commit();            // together with the surplus entries of G_2 / G_3
-        issueC(anc1, p0 + stride, 1u); cp_async_commit();
+        issueC(anc0, zf0, p0, 0u); cp_async_commit();       // together with the surplus entries of G_2 / G_3
+        issueC(anc1, zf1, p0 + stride, 1u); cp_async_commit();
         cp_async_commit();                                   // empty group: iteration 0 waits for all but the two youngest
     }
     unsigned buf = 0u;
@@ -361,7 +423,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
                 const uint32_t zf_cur = stageB(p + 4 * stride, buf);
                 stageA(p + 6 * stride, buf);
                 cp_async_commit();
-                issueC(anc, p + 2 * stride, buf);
+                issueC(anc, zf_old, p + 2 * stride, buf);
                 cp_async_commit();
                 zf_old = zf_new; zf_new = zf_cur;
                 buf ^= 1u;
@@ -631,19 +693,31 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
 // uRSIndices of this island's slots as GLOBAL parent ids (island mode): the same decode as stage B / C of k_step, including
 // surplus entries that live in another island's list (read over NVLink peer memory).
 static __global__ void k_decode_indices_island(AncestorMap am, long long n_loc, const Ctrl* ctrl, IslandInfo isl, uint32_t* idx) {
+    __shared__ uint32_t s_zoff[ISL_MAX + 1], s_eoff[ISL_MAX + 1];
+    if (threadIdx.x < 32) {   // same exchange as at the top of k_step (posting a message twice is harmless)
+        const unsigned long long seq = (isl.epoch << 24) + (unsigned long long)ctrl->T + 1ull;
+        if (blockIdx.x == 0) {
+            double mine[2] = {(double)ctrl->zoff[ISL_MAX + 1], (double)ctrl->eoff[ISL_MAX + 1]};
+            __threadfence_system();
+            island_send(isl, ISL_KIND_ZE, seq, mine, 2);
+        }
+        island_ze_offsets(isl, seq, s_zoff, s_eoff);
+        __threadfence_system();
+    }
+    __syncthreads();
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_loc) return;
     const uint32_t slot_lo = (uint32_t)(isl.rank * isl.n_loc);
     const uint32_t word = am.zmask[s >> 5], bit = (uint32_t)s & 31u;
     uint32_t anc = slot_lo + (uint32_t)s;
     if ((word >> bit) & 1u) {
-        const long long m = ctrl->zoff[isl.rank] + am.zbase[s >> 5] + __popc(word & ((1u << bit) - 1u));
-        if (m >= ctrl->eoff[isl.world]) anc = 0u;   // beyond the available surplus children: particle 0 (sampler.h:845)
+        const uint32_t m = s_zoff[isl.rank] + am.zbase[s >> 5] + __popc(word & ((1u << bit) - 1u));
+        if (m >= s_eoff[isl.world]) anc = 0u;   // beyond the available surplus children: particle 0 (sampler.h:845)
         else {
             int o = 0;
-            while (o + 1 < isl.world && m >= ctrl->eoff[o + 1]) ++o;
+            while (o + 1 < isl.world && m >= s_eoff[o + 1]) ++o;
             const uint32_t* sp = reinterpret_cast<const uint32_t*>(isl.base[o] + isl.off_surplus);
-            anc = sp[m - ctrl->eoff[o]];
+            anc = (uint32_t)(o * isl.n_loc) + sp[m - s_eoff[o]];   // the lists hold ids local to the island that owns them
         }
     }
     idx[s] = anc;
@@ -683,6 +757,7 @@ public:
         { const char* e = getenv("SMCB200_DBG_STEP"); dbg_step_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_DBG_SCAN"); dbg_scan_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_SCAN_IMPL"); scan_impl_ = e ? atoi(e) : 1; }   // 0: block-tiled kernel (A/B measurements)
+        { const char* e = getenv("SMCB200_FORCE_ISLAND"); force_island_ = e && e[0] == '1'; }   // island kernels on ONE rank (profiling their code path without peers)
         ntiles_ = scan_tiles(n);
         surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
         // ---- slab layout (256-byte aligned sub-allocations)
@@ -743,7 +818,7 @@ public:
     Sampler& operator=(const Sampler&) = delete;
 
     // ---- island plumbing: one IPC handle per rank, exchanged by the host (torch.distributed in bench.py / tests)
-    bool island() const { return world_ > 1; }
+    bool island() const { return world_ > 1 || force_island_; }
     int rank() const { return rank_; }
     void ExportIpc(cudaIpcMemHandle_t* out) { SMCB_CUDA(cudaIpcGetMemHandle(out, slab_)); }
     void ImportPeers(const cudaIpcMemHandle_t* handles) {
@@ -989,6 +1064,7 @@ private:
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
     int dbg_step_ = 0, dbg_scan_ = 0, scan_impl_ = 1;
+    bool force_island_ = false;
     double dyn_[4] = {0.0, 0.0, 0.0, 0.0};
     cudaGraphExec_t graph_exec_ = nullptr;
     cudaStream_t graph_stream_ = nullptr;

@@ -374,7 +374,7 @@ __device__ __forceinline__ void resample_scan_body(const ScanArgs& a, ScanSmem& 
     const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
     const double mass0 = ISLAND ? u64_to_double_exact(*a.mass_offset_ptr) * INV_TWO52 : 0.0;   // weight mass of lower ranks
-    const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
+    const uint32_t gslot0 = 0u;   // parent ids are local to the island that owns the list (island mode: the reader adds the owner's offset)
     const long long scap = a.surplus_cap > 0 ? a.surplus_cap : n;
     const int n32 = (int)n;                                // n < 2^31
     // children handed out before this rank's first slot (0 on a single GPU)
@@ -696,6 +696,9 @@ __device__ __forceinline__ void rs_chunk(int ntiles, int& t0, int& t1) {
     t1 = min(t0 + per, ntiles);
 }
 
+#ifndef SMCB_RS_MASS_BPS
+#define SMCB_RS_MASS_BPS 8
+#endif
 template <int SRC, bool ISLAND>
 __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
     pdl_wait_for_predecessor();
@@ -731,29 +734,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
             atomicAdd(V.super_mass + tile / RP_SUPER, (unsigned long long)__double2ll_rn(s * TWO52));
         }
     }
-    if (ISLAND) {
-        // this rank's total mass -> all-gather -> where does this rank's cumulative weight start (mass of the lower ranks)
-        __shared__ bool s_last;
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u; }
-        __syncthreads();
-        if (!s_last || threadIdx.x >= 32) return;
-        __threadfence();
-        const int nsuper = (ntiles + RP_SUPER - 1) / RP_SUPER;
-        unsigned long long tot = 0ull;
-        for (int k = lane; k < nsuper; k += 32) tot += reinterpret_cast<volatile unsigned long long*>(V.super_mass)[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(SMCB_FULL, tot, o);
-        __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
-        double mine[1] = {(double)tot};   // < 2^53: exact
-        island_allgather(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)(*a.step_ptr) + 1ull, mine, 1, s_all);
-        if (lane == 0) {
-            unsigned long long off = 0ull;
-            for (int h = 0; h < a.isl.rank; ++h) off += (unsigned long long)s_all[h][0];
-            *a.mass_offset_out = off;
-            *a.done = 0u;
-        }
-    }
+    // (island mode: the rank's total is posted to the peers by the first block of k_rs_count, from the super masses above)
 }
 
 template <int SRC, int MODE, bool ISLAND, bool POW2>
@@ -770,7 +751,19 @@ __device__ __forceinline__ void rs_count_body(const ScanArgs& a) {
     const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;
     const double dRand = (MODE == SYSTEMATIC) ? (0.0 + (inv_n - 0.0) * (*a.u_ptr)) : 0.0;
     const long long step = a.step_ptr ? *a.step_ptr : 0;
-    const double mass0 = ISLAND ? u64_to_double_exact(*a.mass_offset_ptr) * INV_TWO52 : 0.0;   // weight mass of lower ranks
+    // island mode: weight mass of the lower ranks = where this rank's cumulative weight starts.  Every warp reads the masses the
+    // other ranks' mass passes posted into this rank's mailbox (local memory; they have usually arrived by now)
+    if (ISLAND && blockIdx.x == 0 && threadIdx.x < 32) {
+        // this rank's exact weight mass (sum of the super masses the mass pass accumulated), posted to every rank's mailbox
+        const int nsuper = (ntiles + RP_SUPER - 1) / RP_SUPER;
+        unsigned long long tot = 0ull;
+        for (int k = lane; k < nsuper; k += 32) tot += V.super_mass[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(SMCB_FULL, tot, o);
+        double mine[1] = {(double)tot};   // < 2^53: exact
+        island_send(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)step + 1ull, mine, 1);
+    }
+    const double mass0 = ISLAND ? island_recv_lower_sum(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)step + 1ull) * INV_TWO52 : 0.0;
     const int cstart = ISLAND ? children_upto<MODE, POW2>(mass0, a, nthr, nd, inv_n, dRand, step) : 0;
     int t0, t1;
     rs_chunk(ntiles, t0, t1);
@@ -879,7 +872,7 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_MAP_MINB) k_rs_map(ScanArg
     const int n32 = (int)n;
     const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
     const RsView V = rs_view(a, ntiles);
-    const uint32_t gslot0 = ISLAND ? (uint32_t)(a.isl.rank * a.isl.n_loc) : 0u;                // global id of local slot 0
+    const uint32_t gslot0 = 0u;   // parent ids are local to the island that owns the list (island mode: the reader adds the owner's offset)
     const long long step = a.step_ptr ? *a.step_ptr : 0;
     int t0, t1;
     rs_chunk(ntiles, t0, t1);
@@ -1001,30 +994,8 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_MAP_MINB) k_rs_map(ScanArg
             Z += zagg;
         }
     }
-    if (ISLAND) {
-        // The all-gather of (zero slots, surplus entries) tells every rank's next gather where the m-th zero-count slot of the
-        // GLOBAL order finds its parent -- and it is the signal that this rank's surplus list may be read over NVLink.  It is
-        // therefore sent by the block that FINISHES last, after every block's surplus stores have been fenced at system scope.
-        __shared__ bool s_last;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
-        __syncthreads();
-        if (!s_last || threadIdx.x >= 32) return;
-        __threadfence_system();
-        __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
-        double mine[2] = {(double)*(volatile long long*)&a.zoff_out[ISL_MAX + 1], (double)*(volatile long long*)&a.eoff_out[ISL_MAX + 1]};
-        island_allgather(a.isl, ISL_KIND_ZE, (a.isl.epoch << 24) + (unsigned long long)step + 1ull, mine, 2, s_all);
-        if (lane == 0) {
-            long long z = 0, e = 0;
-            for (int h = 0; h < a.isl.world; ++h) {
-                a.zoff_out[h] = z; a.eoff_out[h] = e;
-                z += (long long)s_all[h][0]; e += (long long)s_all[h][1];
-            }
-            a.zoff_out[a.isl.world] = z; a.eoff_out[a.isl.world] = e;
-            *a.done = 0u;
-        }
-    }
+    // (island mode: the totals stashed above are posted to the peers by the first block of the next k_step -- by then this
+    // whole pass has finished, so their arrival also tells the peers that this rank's surplus list may be read over NVLink)
 }
 
 // Host side: one grid for the three passes (all SMs x resident blocks of the widest kernel, capped by the work available).
@@ -1043,73 +1014,11 @@ inline size_t resample_cslot_entries(long long n) { return (size_t)((n + RP_TILE
 template <int SRC, int MODE, bool ISLAND = false>
 inline void launch_resample_passes(const ScanArgs& a, cudaStream_t stream, const std::function<void()>* after = nullptr) {
     const int grid = resample_pass_grid(a.n);
-    launch_chained(k_rs_mass<SRC, ISLAND>, resample_pass_grid(a.n, 8), RP_THREADS, stream, a);   // pure streaming: more warps in flight
+    launch_chained(k_rs_mass<SRC, ISLAND>, resample_pass_grid(a.n, SMCB_RS_MASS_BPS), RP_THREADS, stream, a);   // pure streaming: more warps in flight
     if (after && *after) (*after)();
     launch_chained(k_rs_count<SRC, MODE, ISLAND>, grid, RP_THREADS, stream, a);
     if (after && *after) (*after)();
     launch_chained(k_rs_map<ISLAND>, resample_pass_grid(a.n, SMCB_RS_MAP_MINB), RP_THREADS, stream, a);
-}
-
-// ---- island mode: integer weight mass of this rank, all-gathered so that every rank knows where its scan starts --------
-struct MassArgs {
-    const double* wt;                    // shifted weights exp(lw - c) written by k_step
-    long long n;
-    const double* inv_s_ptr;             // 1 / their sum over the whole population
-    const int* enable_ptr;
-    const long long* step_ptr;
-    unsigned long long* partial;         // [gridDim.x]
-    unsigned int* done;
-    unsigned long long* mass_offset_out;
-    IslandInfo isl;
-};
-
-static __global__ void __launch_bounds__(256) k_mass_total(MassArgs a) {
-    if (a.enable_ptr && *a.enable_ptr == 0) return;
-    const double inv_s = *a.inv_s_ptr;
-    // Same grid arithmetic as the scan: q = (w + 1) - 1 is w rounded to a multiple of 2^-52, and sums of such values below 2
-    // are exact in fp64 in any order.  Four independent slots per thread and iteration (two 16-byte loads).
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const long long nq = a.n >> 2;
-    const double2* w2 = reinterpret_cast<const double2*>(a.wt);
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nq; i += (long long)gridDim.x * 256) {
-        const double2 u = w2[2 * i], v = w2[2 * i + 1];
-        s0 += (u.x * inv_s + 1.0) - 1.0; s1 += (u.y * inv_s + 1.0) - 1.0;
-        s2 += (v.x * inv_s + 1.0) - 1.0; s3 += (v.y * inv_s + 1.0) - 1.0;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(a.n & 3)) s0 += (a.wt[(nq << 2) + threadIdx.x] * inv_s + 1.0) - 1.0;
-    // every lane total is a multiple of 2^-52 below 2 (the weights sum to 1): the conversions are exact
-    unsigned long long sum = (unsigned long long)__double2ll_rn(s0 * TWO52) + (unsigned long long)__double2ll_rn(s1 * TWO52) +
-                             (unsigned long long)__double2ll_rn(s2 * TWO52) + (unsigned long long)__double2ll_rn(s3 * TWO52);
-    __shared__ unsigned long long s_w[8];
-    __shared__ bool s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(SMCB_FULL, sum, o);
-    if (lane == 0) s_w[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long b = 0ull;
-        for (int w = 0; w < 8; ++w) b += s_w[w];
-        a.partial[blockIdx.x] = b;
-        __threadfence();
-        s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
-    }
-    __syncthreads();
-    if (!s_last || warp != 0) return;
-    __threadfence();
-    unsigned long long tot = 0ull;
-    for (int k = lane; k < (int)gridDim.x; k += 32) tot += reinterpret_cast<volatile unsigned long long*>(a.partial)[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(SMCB_FULL, tot, o);
-    __shared__ double s_all[ISL_MAX][ISL_PAYLOAD];
-    double mine[1] = {(double)tot};   // < 2^53: exact
-    island_allgather(a.isl, ISL_KIND_MASS, (a.isl.epoch << 24) + (unsigned long long)(*a.step_ptr) + 1ull, mine, 1, s_all);
-    if (lane == 0) {
-        unsigned long long off = 0ull;
-        for (int h = 0; h < a.isl.rank; ++h) off += (unsigned long long)s_all[h][0];
-        *a.mass_offset_out = off;
-        *a.done = 0u;
-    }
 }
 
 // ---- counts -> ancestor map (injected counts, multinomial / residual paths) -----------------------------
