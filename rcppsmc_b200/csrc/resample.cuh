@@ -697,7 +697,7 @@ __device__ __forceinline__ void rs_chunk(int ntiles, int& t0, int& t1) {
 }
 
 #ifndef SMCB_RS_MASS_BPS
-#define SMCB_RS_MASS_BPS 8
+#define SMCB_RS_MASS_BPS 12
 #endif
 template <int SRC, bool ISLAND>
 __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
@@ -711,17 +711,34 @@ __global__ void __launch_bounds__(RP_THREADS) k_rs_mass(ScanArgs a) {
     const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
     const double inv_s = (SRC == SRC_WTILDE) ? *a.lse_ptr : 1.0;   // SRC_WTILDE: lse_ptr points at 1 / sum of the shifted weights
     const int nw = (int)(gridDim.x * (RP_THREADS / 32));
-    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
+#ifndef SMCB_RS_MASS_REV
+#define SMCB_RS_MASS_REV 1
+#endif
+    // the next tile's loads are issued before the current tile is reduced (two tiles of a warp in flight)
+    auto tile_of = [&](int it) { return SMCB_RS_MASS_REV ? ntiles - 1 - it : it; };
+    auto load_full = [&](int tile, double2 (&v)[RP_ITEMS / 2]) {
+        const double2* p = reinterpret_cast<const double2*>(a.in + tile * RP_TILE) + lane;
+#pragma unroll
+        for (int r = 0; r < RP_ITEMS / 2; ++r) v[r] = p[32 * r];
+    };
+    const int it0 = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5));
+    double2 vn[RP_ITEMS / 2];
+#pragma unroll
+    for (int r = 0; r < RP_ITEMS / 2; ++r) vn[r] = make_double2(0.0, 0.0);
+    if (it0 < ntiles && tile_of(it0) * RP_TILE + RP_TILE <= n32) load_full(tile_of(it0), vn);
+    for (int it = it0; it < ntiles; it += nw) {
+        const int tile = tile_of(it);
         const int base = tile * RP_TILE;
         double s = 0.0;
         if (base + RP_TILE <= n32) {   // coalesced 16-byte loads; the order inside a tile does not matter for an exact sum
-            const double2* p = reinterpret_cast<const double2*>(a.in + base) + lane;
             double2 v[RP_ITEMS / 2];
 #pragma unroll
-            for (int r = 0; r < RP_ITEMS / 2; ++r) v[r] = p[32 * r];
+            for (int r = 0; r < RP_ITEMS / 2; ++r) v[r] = vn[r];
+            if (it + nw < ntiles && tile_of(it + nw) * RP_TILE + RP_TILE <= n32) load_full(tile_of(it + nw), vn);
 #pragma unroll
             for (int r = 0; r < RP_ITEMS / 2; ++r) s += rs_quantise<SRC>(v[r].x, lse, inv_s) + rs_quantise<SRC>(v[r].y, lse, inv_s);
         } else {
+            if (it + nw < ntiles && tile_of(it + nw) * RP_TILE + RP_TILE <= n32) load_full(tile_of(it + nw), vn);
 #pragma unroll
             for (int r = 0; r < RP_ITEMS; ++r) {
                 const int i = base + r * 32 + lane;
@@ -945,7 +962,34 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_MAP_MINB) k_rs_map(ScanArg
                 uint32_t* seg = s_seg[threadIdx.x >> 5];
                 const uint32_t id0 = gslot0 + (uint32_t)(tile * RP_TILE);     // global id of the tile's first slot
                 uint32_t carry = 0u;                                         // marker (local slot + 1) in force at the window start
+                // A parent with thousands of children (one resampling after a long stretch without: ESS-triggered schemes)
+                // owns a run that spans many windows; the windows that lie entirely inside such a run hold ONE value and are
+                // written with plain 16-byte stores instead of going through the marker scan (measured on pfLineartBS,
+                // 2^20 particles: 1.7 ms -> per resampling pass without this).
+                unsigned hbits = 0u;
+#pragma unroll
+                for (int k = 0; k < RP_ITEMS; ++k) if (cnt[k] - 1 >= 2 * RP_WINDOW) hbits |= 1u << k;
+                const bool tile_heavy = __any_sync(SMCB_FULL, hbits != 0u);
                 for (int w0 = 0; w0 < etile; w0 += RP_WINDOW) {
+                    if (tile_heavy) {
+                        int hend = 0; uint32_t hid = 0u;
+#pragma unroll
+                        for (int k = 0; k < RP_ITEMS; ++k) {
+                            const int rs = lane_off + o[k], re = rs + cnt[k] - 1;
+                            if (((hbits >> k) & 1u) && rs <= w0 && w0 + RP_WINDOW <= re) { hend = re; hid = (uint32_t)(lane * RP_ITEMS + k + 1); }
+                        }
+                        const unsigned hb = __ballot_sync(SMCB_FULL, hend != 0);
+                        if (hb) {
+                            const int src = __ffs(hb) - 1;
+                            hend = __shfl_sync(SMCB_FULL, hend, src);
+                            hid = __shfl_sync(SMCB_FULL, hid, src);
+                            const int wend = w0 + ((hend - w0) / RP_WINDOW) * RP_WINDOW;     // whole windows inside the run
+                            write_surplus_heavy(a.am.surplus, Etile + w0, Etile + wend, id0 + hid - 1u, 0x7fffffffffffffffLL);
+                            carry = hid;
+                            w0 = wend - RP_WINDOW;                                           // the loop adds one window
+                            continue;
+                        }
+                    }
                     const int wlen = min(etile - w0, RP_WINDOW);
                     for (int j = lane; j < wlen; j += 32) seg[j] = 0u;
                     __syncwarp();
