@@ -360,12 +360,17 @@ int smcb200_pfNonlinBS_run(smcb200_pf* h, int resample_mode, double threshold) {
             s.SetAfterLaunchHook(nullptr);
         }
         SMCB_CUDA(cudaEventRecord(h->ev0, h->stream));
-        s.Initialise();
-        for (long t = 1; t < h->T; ++t) s.Iterate();
-        s.ObserveFinal();
+        if (s.SmallEligible()) {   // small populations: the whole filter is one cooperative launch (csrc/small.cuh)
+            s.RunFilterSmall(h->T, true);
+            h->launches = 1;
+        } else {
+            s.Initialise();
+            for (long t = 1; t < h->T; ++t) s.Iterate();
+            s.ObserveFinal();
+            // per step: k_step + the three resampling passes (mass / count / map), or + the four kernels of the draw-based schemes
+            h->launches = h->T * ((resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 4 : 5) + 1;
+        }
         SMCB_CUDA(cudaEventRecord(h->ev1, h->stream));
-        // per step: k_step + the three resampling passes (mass / count / map), or + the four kernels of the draw-based schemes
-        h->launches = h->T * ((resample_mode == SMCB200_SYSTEMATIC || resample_mode == SMCB200_STRATIFIED) ? 4 : 5) + 1;
         h->ran = true;
         return SMCB200_OK;
     });

@@ -723,6 +723,10 @@ static __global__ void k_decode_indices_island(AncestorMap am, long long n_loc, 
     idx[s] = anc;
 }
 
+}  // namespace smcb
+#include "small.cuh"
+namespace smcb {
+
 // Number of persistent blocks for a kernel: all SMs x resident blocks, capped by the work available.
 template <class K>
 inline int persistent_grid(K kernel, int threads, long long work_items, int items_per_block) {
@@ -757,6 +761,7 @@ public:
         { const char* e = getenv("SMCB200_DBG_STEP"); dbg_step_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_DBG_SCAN"); dbg_scan_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_SCAN_IMPL"); scan_impl_ = e ? atoi(e) : 1; }   // 0: block-tiled kernel (A/B measurements)
+        { const char* e = getenv("SMCB200_SMALL_MAX"); if (e) small_max_ = atoll(e); }                  // 0 disables the single-launch path
         { const char* e = getenv("SMCB200_FORCE_ISLAND"); force_island_ = e && e[0] == '1'; }   // island kernels on ONE rank (profiling their code path without peers)
         ntiles_ = scan_tiles(n);
         surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
@@ -853,6 +858,7 @@ public:
     // sampler.h:481-550 (up to and including the resampling decision; the resampling pass itself is enqueued here too)
     void Initialise() {
         if (!peers_ready_) throw std::runtime_error("island sampler: ImportPeers() has not been called");
+        last_small_ = false;
         ++isl_.epoch;
         if (capturing_) {   // graph node: re-uploads whatever the staging copy holds at replay time
             SMCB_CUDA(cudaMemcpyAsync(ctrl_, ctrl_stage_, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
@@ -888,6 +894,7 @@ public:
     // occupancy queries), the graph is rebuilt when the resampling mode, length or injected-draw pointers change.
     // Returns with the filter finished when it was replayed from a graph; an eager run is only enqueued.
     void RunFilter(long long T, bool use_graph = true) {
+        if (SmallEligible()) { RunFilterSmall(T, false); return; }
         GraphKey key{mode_, T, znoise_, ures_, ustrat_, udraw_, {}};
         static_assert(sizeof(typename Model::Params) <= sizeof(key.params), "GraphKey::params too small for this model");
         std::memcpy(key.params, &params_, sizeof(typename Model::Params));   // kernel arguments are baked into the captured nodes
@@ -930,6 +937,42 @@ public:
         SMCB_CUDA(cudaGraphLaunch(graph_exec_, graph_stream_));
         SMCB_CUDA(cudaStreamSynchronize(graph_stream_));
     }
+    // Small populations: the whole filter -- Initialise(); (T - 1) x Iterate(); optionally the closing moment pass -- as ONE
+    // cooperative launch (small.cuh).  Enqueued on the sampler's stream; ReadCtrl / ReadTraces / ReadAncestors work as after the
+    // kernel-per-step path.  Not available in island mode or with a per-launch hook (profiling).
+    bool SmallEligible() const { return small_max_ > 0 && n_ <= small_max_ && !island() && !after_launch_ && !capturing_; }
+    void RunFilterSmall(long long T, bool observe_final) {
+        if (T < 1) throw std::invalid_argument("RunFilterSmall: T >= 1 required");
+        int dev = 0, sms = 0;
+        SMCB_CUDA(cudaGetDevice(&dev));
+        SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int g = (int)((n_ + 2 * SF_THREADS - 1) / (2 * SF_THREADS));
+        if (g > sms) g = sms;
+        if (g > SF_MAXB) g = SF_MAXB;
+        const int k = 2 * (int)((n_ + 2LL * SF_THREADS * g - 1) / (2LL * SF_THREADS * g));
+        if (!sf_enc_) {
+            sf_enc_ = dalloc<int>(n_);
+            if (!count_) count_ = dalloc<int>(n_);
+            if (!cum_) cum_ = dalloc<unsigned long long>(n_);
+            if (!bucket_) bucket_ = dalloc<uint32_t>(draw_bucket_entries(n_));
+            const size_t entries = (size_t)SF_KINDS * 2 * SF_MAXB * SF_NV;
+            sf_sync_ = dalloc<ulonglong2>(entries);
+            SMCB_CUDA(cudaMemsetAsync(sf_sync_, 0, sizeof(ulonglong2) * entries, stream_));
+        }
+        Ctrl h = fresh_ctrl();
+        SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        SmallArgs<Model> a{};
+        for (int d = 0; d < D; ++d) { a.xa[d] = xa_[d]; a.xb[d] = xb_[d]; }
+        a.lw = lw_; a.wt = wt_; a.n = n_; a.enc = sf_enc_; a.surplus = am_.surplus; a.cum = cum_; a.count = count_; a.sync = sf_sync_;
+        a.ctrl = ctrl_; a.tr = tr_; a.params = params_; a.znoise = znoise_; a.ures = ures_; a.ustrat = ustrat_; a.udraw = udraw_;
+        a.tcap = tcap_; a.T = T; a.mode = mode_; a.k = k; a.resid_shift = residual_shift(n_); a.observe_final = observe_final ? 1 : 0;
+        a.run_id = ++sf_run_id_; a.dbg = dbg_step_;
+        void* params[] = {&a};
+        const void* fn = znoise_ ? (const void*)k_filter_small<Model, true> : (const void*)k_filter_small<Model, false>;
+        SMCB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)g), dim3(SF_THREADS), params, 0, stream_));
+        steps_ = T;
+        last_small_ = true;
+    }
     // Fused Integrate for the current (last) population: closes the observable trace.
     void ObserveFinal() {
         StepArgs<Model> a = args();
@@ -961,7 +1004,8 @@ public:
         Ctrl c = ReadCtrl();
         uint32_t* d = dalloc_tmp<uint32_t>(n_);
         if (c.resampled) {
-            if (island()) k_decode_indices_island<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, ctrl_, isl_, d);
+            if (last_small_) k_decode_small<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(sf_enc_, am_.surplus, n_, d);
+            else if (island()) k_decode_indices_island<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, ctrl_, isl_, d);
             else k_decode_indices<<<(unsigned)((n_ + 255) / 256), 256, 0, stream_>>>(am_, n_, d);
             SMCB_CUDA(cudaGetLastError());
             SMCB_CUDA(cudaMemcpyAsync(host_idx, d, sizeof(uint32_t) * n_, cudaMemcpyDeviceToHost, stream_));
@@ -1064,6 +1108,11 @@ private:
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
     int dbg_step_ = 0, dbg_scan_ = 0, scan_impl_ = 1;
+    long long small_max_ = 1 << 18;      // populations up to this size run whole filters through k_filter_small
+    int* sf_enc_ = nullptr;
+    ulonglong2* sf_sync_ = nullptr;
+    unsigned long long sf_run_id_ = 0;
+    bool last_small_ = false;
     bool force_island_ = false;
     double dyn_[4] = {0.0, 0.0, 0.0, 0.0};
     cudaGraphExec_t graph_exec_ = nullptr;
