@@ -947,6 +947,7 @@ public:
         SMCB_CUDA(cudaGetDevice(&dev));
         SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         int g = (int)((n_ + 2 * SF_THREADS - 1) / (2 * SF_THREADS));
+        if (n_ <= 4 * SF_THREADS) g = 1;   // up to 1024 particles: one block, exchanges are block barriers
         if (g > sms) g = sms;
         if (g > SF_MAXB) g = SF_MAXB;
         const int k = 2 * (int)((n_ + 2LL * SF_THREADS * g - 1) / (2LL * SF_THREADS * g));
@@ -955,18 +956,17 @@ public:
             if (!count_) count_ = dalloc<int>(n_);
             if (!cum_) cum_ = dalloc<unsigned long long>(n_);
             if (!bucket_) bucket_ = dalloc<uint32_t>(draw_bucket_entries(n_));
-            const size_t entries = (size_t)SF_KINDS * 2 * SF_MAXB * SF_NV;
-            sf_sync_ = dalloc<ulonglong2>(entries);
-            SMCB_CUDA(cudaMemsetAsync(sf_sync_, 0, sizeof(ulonglong2) * entries, stream_));
+            sf_sync_ = dalloc<unsigned long long>((size_t)SF_KINDS * 2 * SF_MAXB * SF_NV + 16);
         }
+        SMCB_CUDA(cudaMemsetAsync(sf_sync_, 0, sizeof(unsigned long long) * 16, stream_));   // the arrival counter
         Ctrl h = fresh_ctrl();
         SMCB_CUDA(cudaMemcpyAsync(ctrl_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
         SmallArgs<Model> a{};
         for (int d = 0; d < D; ++d) { a.xa[d] = xa_[d]; a.xb[d] = xb_[d]; }
-        a.lw = lw_; a.wt = wt_; a.n = n_; a.enc = sf_enc_; a.surplus = am_.surplus; a.cum = cum_; a.count = count_; a.sync = sf_sync_;
+        a.lw = lw_; a.wt = wt_; a.n = n_; a.enc = sf_enc_; a.surplus = am_.surplus; a.cum = cum_; a.count = count_; a.sync.counter = sf_sync_; a.sync.table = sf_sync_ + 16;
         a.ctrl = ctrl_; a.tr = tr_; a.params = params_; a.znoise = znoise_; a.ures = ures_; a.ustrat = ustrat_; a.udraw = udraw_;
         a.tcap = tcap_; a.T = T; a.mode = mode_; a.k = k; a.resid_shift = residual_shift(n_); a.observe_final = observe_final ? 1 : 0;
-        a.run_id = ++sf_run_id_; a.dbg = dbg_step_;
+        a.dbg = dbg_step_;
         void* params[] = {&a};
         const void* fn = znoise_ ? (const void*)k_filter_small<Model, true> : (const void*)k_filter_small<Model, false>;
         SMCB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)g), dim3(SF_THREADS), params, 0, stream_));
@@ -1108,10 +1108,9 @@ private:
     long long n_, tcap_, ntiles_, n_glob_ = 0, surplus_cap_ = 0;
     int rank_ = 0, world_ = 1;
     int dbg_step_ = 0, dbg_scan_ = 0, scan_impl_ = 1;
-    long long small_max_ = 1 << 18;      // populations up to this size run whole filters through k_filter_small
+    long long small_max_ = 1 << 16;      // populations up to this size run whole filters through k_filter_small (measured break-even with the kernel-per-step path)
     int* sf_enc_ = nullptr;
-    ulonglong2* sf_sync_ = nullptr;
-    unsigned long long sf_run_id_ = 0;
+    unsigned long long* sf_sync_ = nullptr;
     bool last_small_ = false;
     bool force_island_ = false;
     double dyn_[4] = {0.0, 0.0, 0.0, 0.0};

@@ -1,13 +1,13 @@
-// Whole filter in ONE launch for small populations (N <= 2^18): the reference's loop Initialise(); IterateUntil(T-1)
+// Whole filter in ONE launch for small populations (N <= 2^16 by default, SMCB200_SMALL_MAX): the reference's loop Initialise(); IterateUntil(T-1)
 // (inst/include/sampler.h:481-550, :701-764; e.g. the inner filter of src/nonLinPMMH.cpp:78-113, run once per MH iteration).
 //
 // At 10^3..10^5 particles a step's kernels finish faster than they can be launched (measured: 20 us per step with four
 // launches replayed from a CUDA graph at 2^16 particles, 2 % of the HBM roofline).  Here a cooperative grid of at most one
 // block per SM keeps the whole filter on the device: block b owns a contiguous range of slots, thread t a contiguous run of K
 // slots inside it, the population lives in L2, and the steps are separated by EXCHANGES instead of kernel boundaries:
-// every block posts a few values (its partial sums / masses / zero-slot counts) as 16-byte (value, epoch) entries and reads
-// everybody else's -- one L2 round trip, no atomics, nothing to reset -- and then derives the step's scalars itself, in the same
-// fixed order as every other block (so all blocks hold bit-identical values).  Per step: one exchange when the population is
+// every block posts a few values (its partial sums / masses / zero-slot counts) into a table, counts itself in on one monotone
+// counter, and reads everybody else's once all have arrived; it then derives the step's scalars itself, in the same fixed order
+// as every other block (so all blocks hold bit-identical values).  Per step: one exchange when the population is
 // kept, four when it is resampled (SYSTEMATIC / STRATIFIED), six for the draw-based schemes.
 //
 // Same definitions as the large-population kernels (k_step, k_rs_*, k_cum_scan, k_multinomial_draw, k_count_map): Philox
@@ -25,6 +25,11 @@ constexpr int SF_KINDS = 8;             // exchange points of a step (double-buf
 constexpr int SF_HEAVY = 32;            // surplus runs longer than this are written by the whole block
 constexpr int SF_QCAP = 128;            // queue of such runs per block and step
 
+struct SfSync {
+    unsigned long long* table;     // [SF_KINDS][2][SF_MAXB][SF_NV] values posted by the blocks
+    unsigned long long* counter;   // arrivals since the launch (zeroed by the host before every launch)
+};
+
 template <class Model>
 struct SmallArgs {
     double* xa[Model::D];
@@ -36,7 +41,7 @@ struct SmallArgs {
     uint32_t* surplus;          // [n] surplus[m] = parent of the m-th zero-count slot
     unsigned long long* cum;    // [n] inclusive integer scan of the weights (MULTINOMIAL / RESIDUAL)
     int* count;                 // [n] children per parent
-    ulonglong2* sync;           // [SF_KINDS][2][SF_MAXB][SF_NV] exchange entries (value bits, epoch)
+    SfSync sync;
     Ctrl* ctrl;
     Traces tr;
     typename Model::Params params;
@@ -50,7 +55,6 @@ struct SmallArgs {
     int k;                      // slots per thread (even)
     int resid_shift;
     int observe_final;
-    unsigned long long run_id;  // distinguishes the exchanges of this launch from those of earlier ones
     int dbg;
 };
 
@@ -60,36 +64,37 @@ struct SfShared {               // step scalars, identical in every block
     int res;
 };
 
-__device__ __forceinline__ void sf_st16(ulonglong2* p, unsigned long long x, unsigned long long y) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
-__device__ __forceinline__ ulonglong2 sf_ld16(const ulonglong2* p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
 
 // Exchange: thread 0 holds this block's `nv` values (raw 64-bit patterns) in mine[]; afterwards out[b][v] holds every block's.
 // Doubles as a grid-wide barrier with release / acquire semantics for everything the blocks wrote before it.
-// Entries are double-buffered by the parity of the step: a block may post its values of step t+1 while a slower block still
-// reads those of step t, but not those of step t+2 (it cannot get past step t+1 before everybody has posted there).
-__device__ __forceinline__ void sf_exchange(ulonglong2* base, int kind, int par, unsigned long long ep, const unsigned long long* mine, int nv,
+// The values go into a table that is double-buffered by the parity of the step (a block may post its values of step t+1 while
+// a slower block still reads those of step t, but not those of step t+2: it cannot get past step t+1 before everybody has
+// posted there); arrival is counted on ONE monotone counter (`target` = blocks x exchanges so far, the same in every block), so
+// only one thread per block spins, on one address, and the table is read once, without flags.
+__device__ __forceinline__ void sf_exchange(const SfSync& sy, int kind, int par, unsigned long long& target, const unsigned long long* mine, int nv,
                                             unsigned long long (*out)[SF_NV]) {
     const int G = (int)gridDim.x, tid = (int)threadIdx.x;
-    ulonglong2* slots = base + ((size_t)(kind * 2 + par) * SF_MAXB) * SF_NV;
+    if (G == 1) {   // a population that fits one block: the exchange is a block barrier
+        __syncthreads();
+        if (tid == 0) for (int v = 0; v < nv; ++v) out[0][v] = mine[v];
+        __syncthreads();
+        return;
+    }
+    unsigned long long* tab = sy.table + ((size_t)(kind * 2 + par) * SF_MAXB) * SF_NV;
+    target += (unsigned long long)G;
     __syncthreads();
     if (tid == 0) {
+        for (int v = 0; v < nv; ++v) __stcg(tab + (size_t)blockIdx.x * SF_NV + v, mine[v]);
         __threadfence();
-        for (int v = 0; v < nv; ++v) sf_st16(slots + (size_t)blockIdx.x * SF_NV + v, mine[v], ep);
+        atomicAdd(sy.counter, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long*>(sy.counter) < target) { }
+        __threadfence();
     }
+    __syncthreads();
     for (int e = tid; e < G * nv; e += SF_THREADS) {
         const int b = e / nv, v = e - b * nv;
-        const ulonglong2* p = slots + (size_t)b * SF_NV + v;
-        ulonglong2 w = sf_ld16(p);
-        while (w.y != ep) w = sf_ld16(p);
-        out[b][v] = w.x;
+        out[b][v] = __ldcg(tab + (size_t)b * SF_NV + v);
     }
-    __threadfence();
     __syncthreads();
 }
 
@@ -150,7 +155,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
     ScanArgs sa{};                  // what children_upto reads
     sa.ustrat = a.ustrat; sa.seed = seed; sa.seed_ptr = nullptr;
 
-    auto epoch = [&](long long step, int sub) { return (a.run_id << 32) | ((unsigned long long)step << 4) | (unsigned long long)sub; };
+    unsigned long long sync_target = 0ull;   // arrivals the next exchange waits for
+    // profiling switch (SMCB200_DBG_STEP = 64): cycles spent per phase by thread 0 of block 0, printed at the end
+    long long pc[12];
+    for (int i = 0; i < 12; ++i) pc[i] = 0;
+    long long pt = clock64();
+    auto tick = [&](int i) { if ((a.dbg & 64) && blockIdx.x == 0 && tid == 0) { const long long t = clock64(); pc[i] += t - pt; pt = t; } };
     // ancestor of slot s in the population the last step left behind
     auto ancestor = [&](int s, bool resampled) -> int {
         if (!resampled) return s;
@@ -266,7 +276,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
 #pragma unroll
             for (int f = 0; f < NF; ++f) mine[f] = (unsigned long long)__double_as_longlong(v[f]);
         }
-        sf_exchange(a.sync, 0, (int)(step & 1), epoch(step, 0), mine, NF, s_out);
+        tick(0);
+        sf_exchange(a.sync, 0, (int)(step & 1), sync_target, mine, NF, s_out);
+        tick(1);
 
         // ---- phase B: every block closes the step for itself (same order everywhere => same bits everywhere)
         auto merged = [&](double (&v)[NF]) {   // called by warp 0
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
 #pragma unroll
                 for (int f = 0; f < NF; ++f) mine[f] = (unsigned long long)__double_as_longlong(v[f]);
             }
-            sf_exchange(a.sync, 1, (int)(step & 1), epoch(step, 1), mine, NF, s_out);
+            sf_exchange(a.sync, 1, (int)(step & 1), sync_target, mine, NF, s_out);
             if (warp == 0) {
                 double v[NF];
                 merged(v);
@@ -372,6 +384,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
             }
         }
         __syncthreads();
+        tick(2);
         if (observe_only) break;
         parity ^= 1;
         if (!S.res) continue;
@@ -389,7 +402,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
             double btot;
             const double texcl = sf_block_scan<double>(run, s_scan_d, btot);
             if (tid == 0) mine[0] = (unsigned long long)__double_as_longlong(btot);
-            sf_exchange(a.sync, 2, (int)(step & 1), epoch(step, 2), mine, 1, s_out);
+            tick(3);
+            sf_exchange(a.sync, 2, (int)(step & 1), sync_target, mine, 1, s_out);
+            tick(4);
             double P = 0.0, Wtot = 0.0;
             for (int b = 0; b < nb; ++b) { const double m = __longlong_as_double((long long)s_out[b][0]); if (b < (int)blockIdx.x) P += m; Wtot += m; }
             double W = P + texcl;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
             const unsigned long long texcl = sf_block_scan<unsigned long long>(run, s_scan_u, btot);
             (void)sf_block_scan<unsigned long long>(fsum, s_scan_u, ftot);
             if (tid == 0) { mine[0] = btot; mine[1] = ftot; }
-            sf_exchange(a.sync, 2, (int)(step & 1), epoch(step, 2), mine, 2, s_out);
+            sf_exchange(a.sync, 2, (int)(step & 1), sync_target, mine, 2, s_out);
             unsigned long long P = 0ull, Q = 0ull, floor_total = 0ull;
             for (int b = 0; b < nb; ++b) { if (b < (int)blockIdx.x) P += s_out[b][0]; Q += s_out[b][0]; floor_total += s_out[b][1]; }
             unsigned long long cumv = P + texcl;
@@ -446,7 +461,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
                 a.cum[s] = cumv;
                 a.count[s] = (int)fl;
             }
-            sf_exchange(a.sync, 3, (int)(step & 1), epoch(step, 3), mine, 1, s_out);      // cum[] and the floor counts are complete
+            sf_exchange(a.sync, 3, (int)(step & 1), sync_target, mine, 1, s_out);      // cum[] and the floor counts are complete
             // iid draws through the exact integer inverse CDF (same arithmetic as k_multinomial_draw)
             const long long ndraws = resid ? (long long)n - (long long)floor_total : (long long)n;
             for (long long j = (long long)blockIdx.x * SF_THREADS + tid; j < ndraws; j += (long long)nb * SF_THREADS) {
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
                 }
                 atomicAdd(a.count + l, 1);
             }
-            sf_exchange(a.sync, 4, (int)(step & 1), epoch(step, 4), mine, 1, s_out);      // the children counts are complete
+            sf_exchange(a.sync, 4, (int)(step & 1), sync_target, mine, 1, s_out);      // the children counts are complete
             int csum = 0;
             for (int kk = 0; kk < K; ++kk) {
                 const int s = slot0 + kk;
@@ -479,7 +494,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
         int zbt;
         const int zexcl = sf_block_scan<int>(zc, s_scan_i, zbt);
         if (tid == 0) { mine[0] = (unsigned long long)(long long)zbt; mine[1] = 0ull; }
-        sf_exchange(a.sync, 5, (int)(step & 1), epoch(step, 5), mine, 3, s_out);
+        tick(5);
+        sf_exchange(a.sync, 5, (int)(step & 1), sync_target, mine, 3, s_out);
+        tick(6);
         int Zb = 0, ztotal = 0, Cb = 0, ctot_draws = 0;
         for (int b = 0; b < nb; ++b) {
             const int zb = (int)(long long)s_out[b][0], cb = (int)(long long)s_out[b][2];
@@ -526,8 +543,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
             const int etot = ctot - n + ztotal;
             for (int m = max(etot, 0) + tid; m < ztotal; m += SF_THREADS) a.surplus[m] = 0u;
         }
-        sf_exchange(a.sync, 6, (int)(step & 1), epoch(step, 6), mine, 1, s_out);          // the ancestor map is complete
+        tick(7);
+        sf_exchange(a.sync, 6, (int)(step & 1), sync_target, mine, 1, s_out);          // the ancestor map is complete
+        tick(8);
     }
+    if ((a.dbg & 64) && blockIdx.x == 0 && tid == 0)
+        printf("[k_filter_small] n=%d blocks=%d T=%lld cycles/step: A %lld | x0 %lld | B %lld | quantise+scan %lld | x2 %lld | counts %lld | x5 %lld | map %lld | x6 %lld\n",
+               n, nb, a.T, pc[0] / a.T, pc[1] / a.T, pc[2] / a.T, pc[3] / a.T, pc[4] / a.T, pc[5] / a.T, pc[6] / a.T, pc[7] / a.T, pc[8] / a.T);
     if (blockIdx.x == 0 && tid == 0) {
         Ctrl* c = a.ctrl;
         c->lse = S.lse; c->lognc_path = S.path; c->ess = S.ess; c->resampled = S.res; c->inv_s = S.inv_s;
