@@ -761,7 +761,6 @@ public:
         { const char* e = getenv("SMCB200_DBG_STEP"); dbg_step_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_DBG_SCAN"); dbg_scan_ = e ? atoi(e) : 0; }
         { const char* e = getenv("SMCB200_SCAN_IMPL"); scan_impl_ = e ? atoi(e) : 1; }   // 0: block-tiled kernel (A/B measurements)
-        { const char* e = getenv("SMCB200_SMALL_MAX"); if (e) small_max_ = atoll(e); }                  // 0 disables the single-launch path
         { const char* e = getenv("SMCB200_FORCE_ISLAND"); force_island_ = e && e[0] == '1'; }   // island kernels on ONE rank (profiling their code path without peers)
         ntiles_ = scan_tiles(n);
         surplus_cap_ = world > 1 ? n_glob_ : n;   // an island holding most of the mass lists surplus children for everyone
@@ -940,7 +939,11 @@ public:
     // Small populations: the whole filter -- Initialise(); (T - 1) x Iterate(); optionally the closing moment pass -- as ONE
     // cooperative launch (small.cuh).  Enqueued on the sampler's stream; ReadCtrl / ReadTraces / ReadAncestors work as after the
     // kernel-per-step path.  Not available in island mode or with a per-launch hook (profiling).
-    bool SmallEligible() const { return small_max_ > 0 && n_ <= small_max_ && !island() && !after_launch_ && !capturing_; }
+    bool SmallEligible() const {
+        long long cut = small_max_;
+        if (const char* e = getenv("SMCB200_SMALL_MAX")) cut = atoll(e);   // read per call: tests run both paths on one engine (0 = never)
+        return cut > 0 && n_ <= cut && !island() && !after_launch_ && !capturing_;
+    }
     void RunFilterSmall(long long T, bool observe_final) {
         if (T < 1) throw std::invalid_argument("RunFilterSmall: T >= 1 required");
         int dev = 0, sms = 0;
@@ -1094,7 +1097,7 @@ private:
             case MULTINOMIAL:
             case RESIDUAL: {
                 if (!cum_) { cum_ = dalloc<unsigned long long>(n_); count_ = dalloc<int>(n_); bucket_ = dalloc<uint32_t>(draw_bucket_entries(n_)); }
-                DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2, bucket_};
+                DrawWs dw{cum_, count_, &ctrl_->floor_total, &ctrl_->ticket2, bucket_, cslot_};
                 launch_resample_draws<SRC_LOGW>(mode_, lw_, n_, &ctrl_->lse, &ctrl_->resampled, udraw_, &ctrl_->T, seed_,
                                                 &ctrl_->ticket, s.ws, dw, am_, nullptr, stream_, &ctrl_->seed);
                 break;

@@ -1042,6 +1042,108 @@ __global__ void __launch_bounds__(RP_THREADS, SMCB_RS_MAP_MINB) k_rs_map(ScanArg
     // whole pass has finished, so their arrival also tells the peers that this rank's surplus list may be read over NVLink)
 }
 
+// ---- children counts -> (cslot, zero-slot bitmap, tile / super totals): the front half of the ancestor map for the schemes that
+// produce COUNTS (MULTINOMIAL / RESIDUAL draws), in the same streaming structure as the weight passes above; k_rs_map finishes.
+struct CountPassArgs {
+    const int* count;            // [n] children per parent
+    long long n;
+    const int* enable_ptr;
+    ScanWs ws;                   // statusA: tile totals, statusB: tile zero counts, statusC: super totals | super zero counts (zero on entry)
+    AncestorMap am;
+    uint32_t* cslot;
+};
+static __global__ void __launch_bounds__(RP_THREADS) k_cnt_tiles(CountPassArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int n32 = (int)a.n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    unsigned long long* tile_c = a.ws.statusA;
+    unsigned long long* super_c = a.ws.statusC;
+    const int nw = (int)(gridDim.x * (RP_THREADS / 32));
+    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
+        const int base = tile * RP_TILE;
+        int s = 0;
+#pragma unroll
+        for (int r = 0; r < RP_ITEMS; ++r) {
+            const int i = base + r * 32 + lane;
+            if (i < n32) s += a.count[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(SMCB_FULL, s, o);
+        if (lane == 0) {
+            tile_c[tile] = (unsigned long long)s;
+            atomicAdd(super_c + tile / RP_SUPER, (unsigned long long)s);
+        }
+    }
+}
+static __global__ void __launch_bounds__(RP_THREADS) k_cnt_scan(CountPassArgs a) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int n32 = (int)a.n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const unsigned long long* tile_c = a.ws.statusA;
+    const unsigned long long* super_c = a.ws.statusC;
+    unsigned long long* tile_z = a.ws.statusB;
+    unsigned long long* super_z = a.ws.statusC + (ntiles + RP_SUPER - 1) / RP_SUPER;
+    int t0, t1;
+    rs_chunk(ntiles, t0, t1);
+    if (t0 >= t1) return;
+    int C;                                               // children handed out in front of the chunk
+    {
+        const int s0 = t0 / RP_SUPER;
+        unsigned long long acc = 0ull;
+        for (int k = lane; k < s0; k += 32) acc += super_c[k];
+        for (int k = s0 * RP_SUPER + lane; k < t0; k += 32) acc += tile_c[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCB_FULL, acc, o);
+        C = (int)acc;
+    }
+    for (int tile = t0; tile < t1; ++tile) {
+        const int g0 = tile * RP_TILE + lane * RP_ITEMS;
+        const int nv = min(max(n32 - g0, 0), RP_ITEMS);
+        uint32_t c[RP_ITEMS];
+        int run = 0;
+        unsigned zbits = 0u;
+        if (nv == RP_ITEMS) {
+            uint32_t v[8];
+            ld_global_v8(reinterpret_cast<const uint32_t*>(a.count) + g0, v);
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) { if (v[k] == 0u) zbits |= 1u << k; run += (int)v[k]; c[k] = (uint32_t)run; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) {
+                const int v = k < nv ? a.count[g0 + k] : 0;
+                if (k < nv && v == 0) zbits |= 1u << k;
+                run += v; c[k] = (uint32_t)run;
+            }
+        }
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(SMCB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int excl = C + inc - run;
+        C += __shfl_sync(SMCB_FULL, inc, 31);
+#pragma unroll
+        for (int k = 0; k < RP_ITEMS; ++k) c[k] += (uint32_t)excl;
+        st_global_v8(a.cslot + g0, c);                   // padded to whole tiles: no guard
+        {
+            unsigned m = zbits << (8 * (lane & 3));
+            m |= __shfl_xor_sync(SMCB_FULL, m, 1);
+            m |= __shfl_xor_sync(SMCB_FULL, m, 2);
+            if ((lane & 3) == 0 && g0 < n32) a.am.zmask[g0 >> 5] = m;
+        }
+        int z = __popc(zbits);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(SMCB_FULL, z, o);
+        if (lane == 0) {
+            tile_z[tile] = (unsigned long long)z;
+            atomicAdd(super_z + tile / RP_SUPER, (unsigned long long)z);
+        }
+    }
+}
+
 // Host side: one grid for the three passes (all SMs x resident blocks of the widest kernel, capped by the work available).
 inline int resample_pass_grid(long long n, int blocks_per_sm = 3) {
     int dev = 0, sms = 0;
@@ -1361,6 +1463,7 @@ struct DrawWs {                      // extra workspace of the MULTINOMIAL / RES
     unsigned long long* floor_total; // device scalar (zero on entry)
     unsigned int* ticket2;           // second tile ticket (zero on entry)
     uint32_t* bucket;                // [draw_bucket_entries(n)] search guide of the inverse-CDF draws
+    uint32_t* cslot = nullptr;       // [resample_cslot_entries(n)] optional: counts -> map through the streaming passes
 };
 inline size_t draw_bucket_entries(long long n) { return ((size_t)2 << draw_log_buckets(n)) + 2; }
 
@@ -1400,6 +1503,22 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
     need = (n + 255) / 256;
     k_multinomial_draw<<<(int)(need < grid_draw ? need : grid_draw), 256, 0, stream>>>(d);
     SMCB_CUDA(cudaGetLastError());
+    if (dw.cslot) {
+        // counts -> ancestor map as three streaming passes (tile totals / scan + zero-slot bitmap / k_rs_map): 85 us at 2^24 slots
+        // against 326 us for the single-pass look-back kernel below.  statusA is free again (the integer scan is finished),
+        // statusB / statusC are still zero.
+        CountPassArgs cp{dw.count, n, enable_ptr, ws, am, dw.cslot};
+        const int gp = resample_pass_grid(n);
+        k_cnt_tiles<<<resample_pass_grid(n, 8), RP_THREADS, 0, stream>>>(cp);
+        SMCB_CUDA(cudaGetLastError());
+        k_cnt_scan<<<gp, RP_THREADS, 0, stream>>>(cp);
+        SMCB_CUDA(cudaGetLastError());
+        ScanArgs ma{};
+        ma.n = n; ma.enable_ptr = enable_ptr; ma.step_ptr = step_ptr; ma.ws = ws; ma.am = am; ma.cslot = dw.cslot; ma.tail_info = tail_info;
+        k_rs_map<false><<<resample_pass_grid(n, SMCB_RS_MAP_MINB), RP_THREADS, 0, stream>>>(ma);
+        SMCB_CUDA(cudaGetLastError());
+        return;
+    }
     CountMapArgs m{dw.count, n, enable_ptr, dw.ticket2, ws, am, tail_info};
     g = (int)(tiles < grid_map ? tiles : grid_map);
     k_count_map<<<g, SCAN_THREADS, 0, stream>>>(m);
