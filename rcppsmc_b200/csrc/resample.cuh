@@ -1378,6 +1378,111 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cum_scan(CumArgs a) {
     }
 }
 
+// The same integer scan as two streaming passes without inter-block waiting (tile totals, then chunk-local scans from the
+// exact prefix), in the structure of k_rs_mass / k_rs_count: 233 -> about 120 us at 2^24 slots.  Tile totals go to `status`
+// (statusA), super totals are accumulated atomically in `super` (statusB, zero on entry).
+template <int SRC, bool RESID>
+__device__ __forceinline__ unsigned long long cum_value(double raw, double lse, long long n, int shift, unsigned long long& fl) {
+    const double w = (SRC == SRC_LOGW) ? fm_exp(raw - lse) : raw;
+    const unsigned long long q = (unsigned long long)__double2ll_rn(w * TWO52);
+    fl = 0ull;
+    if (!RESID) return q;
+    const unsigned long long hi = __umul64hi(q, (unsigned long long)n), lo = q * (unsigned long long)n;
+    fl = (hi << 12) | (lo >> 52);                                   // floor(n q / 2^52)
+    return (lo & ((1ull << 52) - 1ull)) >> shift;                   // 52-bit fraction, right-shifted
+}
+template <int SRC, bool RESID>
+__global__ void __launch_bounds__(RP_THREADS) k_cum_tiles(CumArgs a, unsigned long long* super) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int n32 = (int)a.n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
+    const int nw = (int)(gridDim.x * (RP_THREADS / 32));
+    unsigned long long fsum = 0ull;
+    for (int tile = (int)(blockIdx.x * (RP_THREADS / 32) + (threadIdx.x >> 5)); tile < ntiles; tile += nw) {
+        const int base = tile * RP_TILE;
+        unsigned long long sum = 0ull;
+#pragma unroll
+        for (int r = 0; r < RP_ITEMS; ++r) {
+            const int i = base + r * 32 + lane;
+            if (i < n32) {
+                unsigned long long fl;
+                sum += cum_value<SRC, RESID>(a.in[i], lse, a.n, a.shift, fl);
+                a.count[i] = (int)fl;
+                fsum += fl;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(SMCB_FULL, sum, o);
+        if (lane == 0) {
+            a.status[tile] = sum;
+            atomicAdd(super + tile / RP_SUPER, sum);
+        }
+    }
+    if (RESID) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(SMCB_FULL, fsum, o);
+        if (lane == 0 && fsum) atomicAdd(a.floor_total, fsum);
+    }
+}
+template <int SRC, bool RESID>
+__global__ void __launch_bounds__(RP_THREADS) k_cum_write(CumArgs a, const unsigned long long* super) {
+    if (a.enable_ptr && *a.enable_ptr == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int n32 = (int)a.n;
+    const int ntiles = (n32 + RP_TILE - 1) / RP_TILE;
+    const double lse = (SRC == SRC_LOGW) ? *a.lse_ptr : 0.0;
+    int t0, t1;
+    rs_chunk(ntiles, t0, t1);
+    if (t0 >= t1) return;
+    unsigned long long P;
+    {
+        const int s0 = t0 / RP_SUPER;
+        unsigned long long acc = 0ull;
+        for (int k = lane; k < s0; k += 32) acc += super[k];
+        for (int k = s0 * RP_SUPER + lane; k < t0; k += 32) acc += a.status[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCB_FULL, acc, o);
+        P = acc;
+    }
+    for (int tile = t0; tile < t1; ++tile) {
+        const int g0 = tile * RP_TILE + lane * RP_ITEMS;
+        const int nv = min(max(n32 - g0, 0), RP_ITEMS);
+        double raw[RP_ITEMS];
+        if (nv == RP_ITEMS) {
+            ld_global_v4(a.in + g0, raw[0], raw[1], raw[2], raw[3]);
+            ld_global_v4(a.in + g0 + 4, raw[4], raw[5], raw[6], raw[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) raw[k] = k < nv ? a.in[g0 + k] : 0.0;
+        }
+        unsigned long long c[RP_ITEMS], run = 0ull;
+#pragma unroll
+        for (int k = 0; k < RP_ITEMS; ++k) {
+            unsigned long long fl;
+            const unsigned long long v = cum_value<SRC, RESID>(raw[k], lse, a.n, a.shift, fl);
+            run += k < nv ? v : 0ull;
+            c[k] = run;
+        }
+        unsigned long long inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(SMCB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const unsigned long long excl = P + inc - run;
+        P += __shfl_sync(SMCB_FULL, inc, 31);
+        if (nv == RP_ITEMS) {
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; k += 2) *reinterpret_cast<ulonglong2*>(a.cum + g0 + k) = make_ulonglong2(excl + c[k], excl + c[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < RP_ITEMS; ++k) if (k < nv) a.cum[g0 + k] = excl + c[k];
+        }
+    }
+}
+
 struct DrawArgs {
     const unsigned long long* cum;   // [n] inclusive integer scan
     long long n;
@@ -1490,7 +1595,11 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
     c.in = in; c.n = n; c.lse_ptr = lse_ptr; c.enable_ptr = enable_ptr; c.ticket = ticket; c.status = ws.statusA;
     c.cum = dw.cum; c.count = dw.count; c.floor_total = dw.floor_total; c.shift = residual_shift(n);
     int g = (int)(tiles < grid_cum ? tiles : grid_cum);
-    if (mode == RESIDUAL) k_cum_scan<SRC, true><<<g, SCAN_THREADS, 0, stream>>>(c);
+    if (dw.cslot) {   // engine path: streaming passes (tile totals in statusA, super totals in statusB; both free again afterwards)
+        const int g1 = resample_pass_grid(n, 8), g2 = resample_pass_grid(n);
+        if (mode == RESIDUAL) { k_cum_tiles<SRC, true><<<g1, RP_THREADS, 0, stream>>>(c, ws.statusB); k_cum_write<SRC, true><<<g2, RP_THREADS, 0, stream>>>(c, ws.statusB); }
+        else { k_cum_tiles<SRC, false><<<g1, RP_THREADS, 0, stream>>>(c, ws.statusB); k_cum_write<SRC, false><<<g2, RP_THREADS, 0, stream>>>(c, ws.statusB); }
+    } else if (mode == RESIDUAL) k_cum_scan<SRC, true><<<g, SCAN_THREADS, 0, stream>>>(c);
     else k_cum_scan<SRC, false><<<g, SCAN_THREADS, 0, stream>>>(c);
     SMCB_CUDA(cudaGetLastError());
     DrawArgs d{};
