@@ -193,6 +193,13 @@ int smcb200_blockpfGaussianOpt(const double* data_host, long n_data, long partic
                                const double* noise_host, const double* uniforms_host, double* weight_host, double* values_host,
                                double* lognc_host, double* ess_host, int* resampled_host, uint32_t* ancestors_host);
 
+/* Same filter, path matrix left on the device (replaces nothing in the reference, whose List(weight, values, logNC) always
+ * returns N x T doubles to R, src/blockpfgaussianopt.cpp:70): values_dev is a DEVICE pointer to particles x n_data doubles,
+ * column-major like values_host.  The other outputs are host buffers as above (any of them may be NULL except values_dev). */
+int smcb200_blockpfGaussianOpt_device(const double* data_host, long n_data, long particles, long lag, uint64_t seed,
+                                      double* weight_host, double* values_dev, double* lognc_host, double* ess_host,
+                                      int* resampled_host);
+
 /* ---- conditional SMC (reference inst/include/conditionalSampler.h, src/cSMCexamples.cpp, sampler.h:445-476) ------------ */
 
 /* Conditional bootstrap particle filters on the scalar linear-Gaussian model of the reference example

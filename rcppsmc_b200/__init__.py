@@ -8,10 +8,10 @@ call raises ``SmcError`` when the CUDA extension or a device is missing.
 """
 from ._native import (  # noqa: F401
     MULTINOMIAL, RESIDUAL, STRATIFIED, SYSTEMATIC, SmcError, PfNonlinBS, lib, lib_path, device_count,
-    log_sum_exp, fastmath_eval, resample, philox4x32, philox4x32_device, philox_normals, pfNonlinBS, pfLineartBS, LinReg, LinRegLA, LinRegLA_adapt, nonLinPMMH, blockpfGaussianOpt, compareNCestimates, conditionalBPF, lgssBPF, ancestor_lines,
+    log_sum_exp, fastmath_eval, resample, philox4x32, philox4x32_device, philox_normals, pfNonlinBS, pfLineartBS, LinReg, LinRegLA, LinRegLA_adapt, nonLinPMMH, blockpfGaussianOpt, blockpfGaussianOpt_device, compareNCestimates, conditionalBPF, lgssBPF, ancestor_lines,
 )
 
 __all__ = [
     "MULTINOMIAL", "RESIDUAL", "STRATIFIED", "SYSTEMATIC", "SmcError", "PfNonlinBS", "lib", "lib_path",
-    "device_count", "log_sum_exp", "fastmath_eval", "resample", "philox4x32", "philox4x32_device", "philox_normals", "pfNonlinBS", "pfLineartBS", "LinReg", "LinRegLA", "LinRegLA_adapt", "nonLinPMMH", "blockpfGaussianOpt", "compareNCestimates", "conditionalBPF", "lgssBPF", "ancestor_lines",
+    "device_count", "log_sum_exp", "fastmath_eval", "resample", "philox4x32", "philox4x32_device", "philox_normals", "pfNonlinBS", "pfLineartBS", "LinReg", "LinRegLA", "LinRegLA_adapt", "nonLinPMMH", "blockpfGaussianOpt", "blockpfGaussianOpt_device", "compareNCestimates", "conditionalBPF", "lgssBPF", "ancestor_lines",
 ]

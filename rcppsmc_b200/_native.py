@@ -62,6 +62,8 @@ def lib():
                                      ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]
     L.smcb200_LinReg.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, ctypes.c_long, _c_double_p, ctypes.c_long,
                                  _c_double_p, _c_double_p, _c_double_p, _c_double_p]
+    L.smcb200_blockpfGaussianOpt_device.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, ctypes.c_void_p,
+                                                    _c_double_p, _c_double_p, _c_int_p]
     L.smcb200_blockpfGaussianOpt.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_uint64, _c_double_p, _c_double_p,
                                              _c_double_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_uint_p]
     L.smcb200_conditionalBPF.argtypes = [_c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
@@ -320,6 +322,18 @@ def blockpfGaussianOpt(data, particles, lag, seed=1, noise=None, uniforms=None, 
     if diagnostics:
         out.update(ESS=ess, resampled=rs, ancestors=anc)
     return out
+
+
+def blockpfGaussianOpt_device(data, particles, lag, values_dev, seed=1):
+    """``blockpfGaussianOpt`` with the [N x T] path matrix left on the GPU: ``values_dev`` is a device pointer (int) to
+    particles x T doubles, column-major (e.g. ``torch.empty((T, N), dtype=torch.float64, device="cuda").data_ptr()``).
+    Returns weight [N], logNC, ESS [T], resampled [T] in host arrays."""
+    y = _f64(np.asarray(data).reshape(-1))
+    T, N = y.size, int(particles)
+    w, nc, ess, rs = np.empty(N), np.empty(1), np.empty(T), np.empty(T, dtype=np.int32)
+    _check(lib().smcb200_blockpfGaussianOpt_device(_dp(y), T, N, int(lag), seed, _dp(w), ctypes.c_void_p(int(values_dev)), _dp(nc), _dp(ess),
+                                                   rs.ctypes.data_as(_c_int_p)))
+    return {"weight": w, "logNC": float(nc[0]), "ESS": ess, "resampled": rs}
 
 
 def _lgss_par(parInits):

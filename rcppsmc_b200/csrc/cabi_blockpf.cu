@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_bpf_collect(BpfArgs a, double* weight, 
 
 void run_blockpf(const double* y_host, long T, long particles, long lag, uint64_t seed, const double* noise_host,
                  const double* unif_host, double* weight, double* values, double* lognc, double* ess_out, int* res_out,
-                 uint32_t* anc_out) {
+                 uint32_t* anc_out, double* values_dev = nullptr) {
     if (!y_host || T < 1 || particles < 1 || lag < 1) throw std::invalid_argument("blockpfGaussianOpt: need data, particles >= 1, lag >= 1");
     if (particles >= (1LL << 31)) throw std::invalid_argument("blockpfGaussianOpt: particles must be < 2^31 (sampler.h:91-95 index width)");
     require_device();
@@ -230,13 +230,16 @@ void run_blockpf(const double* y_host, long T, long particles, long lag, uint64_
         k_bpf_decode<<<grid, 256, 0, st>>>(a, am);
         SMCB_CUDA(cudaGetLastError());
     }
-    DevBuf d_w(weight ? sizeof(double) * n : 0), d_v(values ? sizeof(double) * (size_t)T * n : 0);
-    k_bpf_collect<<<grid, 256, 0, st>>>(a, weight ? d_w.as<double>() : nullptr, values ? d_v.as<double>() : nullptr);
+    // the path matrix goes to the caller's DEVICE buffer when one is given (nothing of size N x T crosses PCIe), else to a
+    // staging buffer that is copied to the host
+    DevBuf d_w(weight ? sizeof(double) * n : 0), d_v(values && !values_dev ? sizeof(double) * (size_t)T * n : 0);
+    double* vdst = values_dev ? values_dev : (values ? d_v.as<double>() : nullptr);
+    k_bpf_collect<<<grid, 256, 0, st>>>(a, weight ? d_w.as<double>() : nullptr, vdst);
     SMCB_CUDA(cudaGetLastError());
     SMCB_CUDA(cudaStreamSynchronize(st));
     SMCB_CUDA(cudaMemcpy(&h, ctrl.p, sizeof h, cudaMemcpyDeviceToHost));
     if (weight) SMCB_CUDA(cudaMemcpy(weight, d_w.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    if (values) SMCB_CUDA(cudaMemcpy(values, d_v.p, sizeof(double) * (size_t)T * n, cudaMemcpyDeviceToHost));
+    if (values && !values_dev) SMCB_CUDA(cudaMemcpy(values, d_v.p, sizeof(double) * (size_t)T * n, cudaMemcpyDeviceToHost));
     if (lognc) *lognc = h.path;
     if (ess_out) SMCB_CUDA(cudaMemcpy(ess_out, ess_tr.p, sizeof(double) * T, cudaMemcpyDeviceToHost));
     std::vector<int> rs(T);
@@ -260,6 +263,20 @@ extern "C" int smcb200_blockpfGaussianOpt(const double* data_host, long n_data, 
     return guarded([&]() -> int {
         run_blockpf(data_host, n_data, particles, lag, seed, noise_host, uniforms_host, weight_host, values_host, lognc_host,
                     ess_host, resampled_host, ancestors_host);
+        return SMCB200_OK;
+    });
+}
+
+// Same filter with the path matrix left on the device: values_dev is a DEVICE pointer to particles x n_data doubles (column-major,
+// as values_host above).  For callers that keep working on the GPU (smoothing functionals, further kernels): the reference's
+// List(weight, values, logNC) costs 8 N T bytes over PCIe, which at 2^20 paths x 100 steps is twice the time of the filter itself.
+extern "C" int smcb200_blockpfGaussianOpt_device(const double* data_host, long n_data, long particles, long lag, uint64_t seed,
+                                                 double* weight_host, double* values_dev, double* lognc_host, double* ess_host,
+                                                 int* resampled_host) {
+    return guarded([&]() -> int {
+        if (!values_dev) throw std::invalid_argument("smcb200_blockpfGaussianOpt_device: values_dev (device pointer) required");
+        run_blockpf(data_host, n_data, particles, lag, seed, nullptr, nullptr, weight_host, nullptr, lognc_host, ess_host, resampled_host,
+                    nullptr, values_dev);
         return SMCB200_OK;
     });
 }

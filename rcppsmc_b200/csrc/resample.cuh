@@ -1579,10 +1579,14 @@ inline void launch_resample_draws(int mode, const double* in, long long n, const
                                   const double* uniforms, const long long* step_ptr, unsigned long long seed,
                                   unsigned int* ticket, const ScanWs& ws, const DrawWs& dw, const AncestorMap& am,
                                   unsigned int* tail_info, cudaStream_t stream, const unsigned long long* seed_ptr = nullptr) {
-    static int grid_cum = 0, grid_map = 0, grid_draw = 0;
+    // launch grids of the current device (cached per device: one process may drive several)
+    static int grids[64][3] = {};
+    int dev = 0;
+    SMCB_CUDA(cudaGetDevice(&dev));
+    int (&gd)[3] = grids[dev & 63];
+    int &grid_cum = gd[0], &grid_map = gd[1], &grid_draw = gd[2];
     if (!grid_cum) {
-        int dev = 0, sms = 0, b = 0;
-        SMCB_CUDA(cudaGetDevice(&dev));
+        int sms = 0, b = 0;
         SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_cum_scan<SRC, false>, SCAN_THREADS, 0));
         grid_cum = sms * (b < 1 ? 1 : b);

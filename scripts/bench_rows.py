@@ -86,7 +86,7 @@ y = H.sim_nonlin(T, 7, var_init=5.0, cos_offset=0.0)[1]
 t = best_of(lambda: smc.nonLinPMMH(y, N, M, seed=9), reps=1)
 row = {"row": "nonLinPMMH", "config": "2^16-particle filters x 500 observations, 200 MH iterations (201 filters), multinomial / 0.5, one chain", "gpu_seconds": t,
        "filters_per_s": (M + 1) / t, "particle_steps_per_s": (M + 1) * N * T / t,
-       "note": "each filter is one replay of a captured CUDA graph (4 kernels per step); ~0.26 s one-off capture cost included; chains shard one per GPU"}
+       "note": "each filter is ONE launch of k_filter_small (csrc/small.cuh); chains shard one per GPU"}
 if have_ref:
     tc = cpu_time(lambda: H.r_pmmh(y, 1 << 13, 2, 3))
     row["cpu_reference"] = {"particle_steps_per_s": 3 * (1 << 13) * T / tc, "cores": 1, "sample": f"2^13-particle filters x 500 obs, 3 filters, {tc:.1f} s"}
@@ -109,6 +109,16 @@ if have_ref:
     tc = cpu_time(lambda: R.smcref_blockpf(dp(H.f64(y)), L(T), L(Nc), L(lag), dp(w), dp(v), dp(nc1)))
     row["cpu_reference"] = {"particle_steps_per_s": Nc * T / tc, "cores": 1, "sample": f"2^13 particles x 100 steps, {tc:.1f} s"}
 rows.append(row)
+try:
+    import torch
+    buf = torch.empty((T, N), dtype=torch.float64, device="cuda")
+    t = best_of(lambda: smc.blockpfGaussianOpt_device(y, N, lag, buf.data_ptr(), seed=3), reps=2)
+    rows.append({"row": "blockpfGaussianOpt (paths left on the device)", "config": "2^20 path-valued particles x 100 steps, lag 5, systematic, ESS < N/2",
+                 "gpu_seconds": t, "particle_steps_per_s": N * T / t, "alg_bytes_per_particle_step": alg, "roofline_frac": N * T * alg / t / 1e9 / PEAK,
+                 "note": "smcb200_blockpfGaussianOpt_device: weights, logNC, ESS to the host, the [N x T] path matrix stays in HBM"})
+    del buf
+except ImportError:
+    pass
 
 # ---- compareNCestimates: 1000 particles, 100 simulations x (4 plain + 4 conditional) filters --------------------------------
 T, N, S = 50, 1000, 100

@@ -69,3 +69,17 @@ def test_large_population_runs_and_is_reproducible(smc):
     # every path is a genealogy: after a resampled step the old rows of children equal the rows of their parents
     small = H.o_blockpf(y, 512, lag, seed=1)
     assert abs(a["logNC"] - small["logNC"]) < 5.0
+
+
+def test_device_resident_paths_equal_host_call(smc):
+    """smcb200_blockpfGaussianOpt_device: the [N x T] path matrix stays on the GPU; same bits as the host-buffer call"""
+    torch = pytest.importorskip("torch")
+    T, N, lag = 30, 5000, 4
+    y = H.sim_lg(T, 3, 10.0)
+    ref = smc.blockpfGaussianOpt(y, N, lag, seed=11, diagnostics=True)
+    buf = torch.empty((T, N), dtype=torch.float64, device="cuda")
+    got = smc.blockpfGaussianOpt_device(y, N, lag, buf.data_ptr(), seed=11)
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().T, ref["values"])
+    assert np.array_equal(got["weight"], ref["weight"]) and got["logNC"] == ref["logNC"]
+    assert np.array_equal(got["resampled"], ref["resampled"])
