@@ -234,7 +234,8 @@ int smcb200_resample(int mode, const double* weights_host, long n, const double*
                 DevBuf cum(sizeof(unsigned long long) * n), extra(sizeof(unsigned long long) * 2);
                 SMCB_CUDA(cudaMemset(extra.p, 0, sizeof(unsigned long long) * 2));
                 DevBuf bucket(sizeof(uint32_t) * draw_bucket_entries(n));
-                DrawWs dw{cum.as<unsigned long long>(), counts.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1), bucket.as<uint32_t>()};
+                DrawWs dw{cum.as<unsigned long long>(), counts.as<int>(), extra.as<unsigned long long>(), (unsigned int*)(extra.as<unsigned long long>() + 1), bucket.as<uint32_t>(),
+                          cslot.as<uint32_t>()};   // the streaming passes of the engine path (integer scan, sorted draws, counts -> map)
                 launch_resample_draws<SRC_WEIGHTS>(mode, w.as<double>(), n, nullptr, nullptr, us.as<double>(), nullptr, 0, ticket, ws, dw, am, tail, 0);
                 SMCB_CUDA(cudaDeviceSynchronize());
             }
