@@ -2,6 +2,7 @@
 // with nvcc (-gencode arch=compute_100a,code=sm_100a).  It replaces, for a model written as __host__ __device__ functors,
 //   smc::sampler<Space,Params>          inst/include/sampler.h:133-237
 //   smc::moveset<Space,Params>          inst/include/moveset.h:73-96        (the four per-particle functions = static members of Model)
+//   smc::conditionalSampler<Space,Params>  inst/include/conditionalSampler.h:39-155
 //   smc::adaptMethods<Space,Params>     inst/include/adaptMethods.h:45-51
 //   smc::staticModelAdapt               inst/include/staticModelAdapt.h:37-171
 //   ResampleType / HistoryType / PathSamplingType                          inst/include/sampler.h:45-68
@@ -23,6 +24,7 @@
 // integrands are functor objects instead of function pointers + void* (the functor's members are the auxiliary data).
 #pragma once
 #include "../../rcppsmc_b200/csrc/generic.cuh"
+#include "../../rcppsmc_b200/csrc/csmc.cuh"
 
 namespace ResampleType { enum Enum { MULTINOMIAL = 0, RESIDUAL, STRATIFIED, SYSTEMATIC }; }   // sampler.h:45-51
 namespace HistoryType { enum Enum { NONE = 0, RAM, AL }; }                                    // sampler.h:61-66
@@ -45,6 +47,22 @@ public:
     using Base::IntegratePathSampling;
     template <class F, class W> double IntegratePathSampling(PathSamplingType::Enum type, F f, W width) { return Base::IntegratePathSampling((int)type, f, width); }
     template <class F, class W> double IntegratePathSampling(F f, W width) { return Base::IntegratePathSampling((int)PathSamplingType::TRAPEZOID2, f, width); }   // sampler.h:201
+};
+
+// smc::conditionalSampler<Space,Params> (inst/include/conditionalSampler.h:39-155) for a model with the device functors
+//   init(x, logw, params, z) / move(t, x, logw, params, z) / weight(t, x, logw, params)     (z = the call's standard normals)
+// and constexpr D, NZ_INIT, NZ_MOVE: conditional resampling with all four ResampleType schemes (conditionalSampler.h:377-655),
+// the reference particle pinned by DoConditionalMove (moveset.h:170-180), HistoryType::AL ancestry.  One object is one chain whose
+// reference-slot indices carry over between runs; a whole run executes as ONE kernel launch of one thread block.
+template <class Model>
+class conditionalSampler : public smcb::ConditionalSampler<Model> {
+    using Base = smcb::ConditionalSampler<Model>;
+public:
+    using Space = typename Base::Space;
+    conditionalSampler(long lSize, HistoryType::Enum htHistoryMode, const std::vector<Space>& referenceTrajectoryInit, unsigned long long seed = 1,
+                       cudaStream_t stream = 0)
+        : Base(lSize, (int)htHistoryMode, referenceTrajectoryInit, seed, stream) {}
+    void SetResampleParams(ResampleType::Enum rtMode, double dThreshold) { Base::SetResampleParams((int)rtMode, dThreshold); }
 };
 
 // Adaptation helpers for likelihood-tempered static models (staticModelAdapt.h:37-171), evaluated on the device through the

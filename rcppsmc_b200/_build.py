@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsmcb200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("cabi.cu", "cabi_lineart.cu", "cabi_linreg.cu", "cabi_pmmh.cu", "cabi_blockpf.cu", "cabi_csmc.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("small.cuh", "generic.cuh", "common.cuh", "fastmath.cuh", "philox.cuh", "resample.cuh", "engine.cuh", "models.cuh", "cabi_common.cuh", "island.cuh", "la_engine.cuh")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("csmc.cuh", "small.cuh", "generic.cuh", "common.cuh", "fastmath.cuh", "philox.cuh", "resample.cuh", "engine.cuh", "models.cuh", "cabi_common.cuh", "island.cuh", "la_engine.cuh")]
 HEADERS.append(os.path.join(ROOT, "include", "smcb200.h"))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -17,254 +17,12 @@
 
 #include "cabi_common.cuh"
 #include "models.cuh"
+#include "csmc.cuh"
 
 using namespace smcb;
 using namespace smcb_abi;
 
 namespace {
-
-constexpr int CS_THREADS = 512;
-
-struct CsmcArgs {
-    LGSS::Params mp;
-    long long T, n;
-    long long n_chains, runs_per_chain;
-    const int* modes;        // [n_chains * runs_per_chain]
-    const double* ref;       // [n_chains * runs_per_chain][T]
-    unsigned long long seed;
-    const double* zin;       // [runs][T][n] or null
-    const double* uin;       // [runs][T][n + 2] or null: {K_t draw, systematic V, offspring i -> 2 + i}
-    // per-chain scratch
-    double* xa; double* xb; double* lw; double* w; double* W; double* P;
-    int* L; uint32_t* anc; uint32_t* refidx;
-    // outputs
-    double* lognc;           // [runs]
-    uint32_t* refidx_out;    // [runs][T]
-    uint32_t* anc_out;       // [runs][T][n] or null  (AL history)
-    double* val_out; double* lw_out;
-    int* res_out;            // [runs][T] or null
-};
-
-struct Shared {
-    double red[3][CS_THREADS / 32];
-    double scan_d[CS_THREADS];
-    int scan_i[CS_THREADS];
-    double bc[4];
-    long long bi[2];
-};
-
-// in-place inclusive scan of a[0..n) by the whole CTA (thread t owns a contiguous chunk); returns the total
-template <class V>
-__device__ V cta_scan(V* a, long long n, V* part) {
-    const int B = blockDim.x, tid = threadIdx.x;
-    const long long c = (n + B - 1) / B, lo = tid * c, hi = lo + c < n ? lo + c : n;
-    V s = 0;
-    for (long long i = lo; i < hi; ++i) s += a[i];
-    part[tid] = s;
-    __syncthreads();
-    for (int off = 1; off < B; off <<= 1) {
-        V v = tid >= off ? part[tid - off] : (V)0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    V run = tid > 0 ? part[tid - 1] : (V)0;
-    const V total = part[B - 1];
-    for (long long i = lo; i < hi; ++i) { run += a[i]; a[i] = run; }
-    __syncthreads();
-    return total;
-}
-
-// Rcpp::sample(n, 1, ., p) on the running sums C of p (restated as in the oracle: first k < n-1 with u <= C_k / C_{n-1}, else n-1)
-__device__ __forceinline__ long long sample_cdf(const double* C, long long n, double tot, double u) {
-    long long lo = 0, hi = n - 1;
-    while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (u <= C[mid] / tot) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-// first j with W[j] > u, clamped to n-1 (arma::find(W.tail(...) > u, 1, "first"), conditionalSampler.h:476,550)
-__device__ __forceinline__ long long first_above(const double* W, long long n, double u) {
-    long long lo = 0, hi = n - 1;
-    while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (W[mid] > u) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ double cs_uniform(const CsmcArgs& a, long long run, long long t, long long slot) {
-    if (a.uin) return a.uin[((size_t)run * (size_t)a.T + (size_t)t) * (size_t)(a.n + 2) + (size_t)slot];
-    return u64_to_unit(philox_draw(a.seed, STREAM_RESAMPLE, (uint32_t)t, (uint64_t)slot, (uint32_t)run).a);
-}
-
-__global__ void __launch_bounds__(CS_THREADS) k_csmc_chain(CsmcArgs a) {
-    __shared__ Shared sh;
-    const int tid = threadIdx.x, B = CS_THREADS, lane = tid & 31, warp = tid >> 5;
-    const long long n = a.n, T = a.T, chain = blockIdx.x;
-    double* xs[2] = {a.xa + chain * n, a.xb + chain * n};
-    double* lw = a.lw + chain * n;
-    double* w = a.w + chain * n;
-    double* W = a.W + chain * n;
-    double* P = a.P + chain * n;
-    int* Lx = a.L + chain * n;
-    uint32_t* anc = a.anc + chain * n;
-    uint32_t* refidx = a.refidx + chain * T;
-    const double log_n = log((double)n), thr = 0.5 * (double)n, nd = (double)n;
-    for (long long t = tid; t < T; t += B) refidx[t] = 0u;   // a fresh sampler object: arma::fill::zeros (conditionalSampler.h:96)
-    __syncthreads();
-
-    for (long long r = 0; r < a.runs_per_chain; ++r) {
-        const long long run = chain * a.runs_per_chain + r;
-        const int mode = a.modes[run];
-        const double* ref = a.ref + (size_t)run * (size_t)T;
-        double path = 0.0, lse_prev = 0.0;
-        int resampled = 0, cur = 0;
-        for (long long t = 0; t < T; ++t) {
-            // ---- DoInit / DoMove over every slot (through the previous step's ancestors), then the pin of the reference slot
-            if (t == 0 && tid == 0) refidx[0] = 0u;
-            __syncthreads();
-            const uint32_t pin = refidx[t];
-            const double* src = xs[cur];
-            double* dst = xs[cur ^ 1];
-            LseAcc<0> acc; acc.clear();
-            for (long long i = tid; i < n; i += B) {
-                double z;
-                if (a.zin) z = a.zin[((size_t)run * (size_t)T + (size_t)t) * (size_t)n + (size_t)i];
-                else { double z1; philox_normal2(a.seed, t == 0 ? STREAM_INIT : STREAM_MOVE, (uint32_t)t, (uint64_t)i, (uint32_t)run, z, z1); }
-                double x, l;
-                if (t == 0) {
-                    x = a.mp.phi * a.mp.x0 + (0.0 + a.mp.sd_evol * z);
-                    l = LGSS::loglik(a.mp, a.mp.y[0], x);
-                } else {
-                    const double xp = resampled ? src[anc[i]] : src[i];
-                    l = resampled ? -log_n : lw[i] - lse_prev;
-                    x = a.mp.phi * xp + (0.0 + a.mp.sd_evol * z);
-                    l += LGSS::loglik(a.mp, a.mp.y[t], x);
-                }
-                if ((uint32_t)i == pin) { x = ref[t]; l += LGSS::loglik(a.mp, a.mp.y[t], x); }   // pfWeight adds (cSMCexamples.cpp:203-210)
-                if (t == 0) l -= log_n;
-                dst[i] = x; lw[i] = l;
-                acc.add(l, nullptr);
-            }
-            cur ^= 1;
-            // ---- logNC increment, ESS (sampler.h:241, :413-417)
-            acc.warp_reduce();
-            if (lane == 0) { sh.red[0][warp] = acc.m; sh.red[1][warp] = acc.s; sh.red[2][warp] = acc.q; }
-            __syncthreads();
-            if (warp == 0) {
-                LseAcc<0> b; b.clear();
-                if (lane < B / 32) { b.m = sh.red[0][lane]; b.s = sh.red[1][lane]; b.q = sh.red[2][lane]; }
-                b.warp_reduce();
-                if (lane == 0) { sh.bc[0] = b.m + log(b.s); sh.bc[1] = (b.s * b.s) / b.q; }
-            }
-            __syncthreads();
-            const double lse = sh.bc[0], ess = sh.bc[1];
-            path += lse;
-            lse_prev = lse;
-            resampled = ess < thr ? 1 : 0;
-            const long long wr = t == 0 ? 1 : t;                      // referenceTrajectoryIndices.at(T + 1), the sampler's own T
-            const uint32_t kt1 = refidx[t == 0 ? 0 : t - 1];
-            double* x = xs[cur];
-            if (!resampled) {
-                if (tid == 0 && wr < T) refidx[wr] = kt1;             // conditionalSampler.h:329-333
-            } else {
-                for (long long i = tid; i < n; i += B) { w[i] = exp(lw[i] - lse); W[i] = w[i]; }
-                __syncthreads();
-                if (mode == MULTINOMIAL) {                            // :385-414
-                    const double tot = cta_scan(W, n, sh.scan_d);
-                    for (long long i = tid; i < n; i += B)
-                        anc[i] = i == 0 ? kt1 : (uint32_t)sample_cdf(W, n, tot, cs_uniform(a, run, t, 2 + i));
-                    if (tid == 0 && wr < T) refidx[wr] = 0u;
-                } else if (mode == STRATIFIED || mode == SYSTEMATIC) { // :416-556
-                    cta_scan(W, n, sh.scan_d);
-                    const double hi = W[kt1], lo = kt1 > 0 ? W[kt1 - 1] : 0.0, wk = w[kt1];
-                    for (long long i = tid; i < n; i += B) {
-                        const double up = (double)(i + 1) / nd, dn = (double)i / nd;
-                        const double s = fmin(hi, up) - fmax(lo, dn);
-                        P[i] = (s > 0.0 ? s : 0.0) / wk;
-                    }
-                    __syncthreads();
-                    const double ptot = cta_scan(P, n, sh.scan_d);
-                    if (tid == 0) {
-                        const long long Kt = sample_cdf(P, n, ptot, cs_uniform(a, run, t, 0));
-                        sh.bi[0] = Kt;
-                        if (mode == SYSTEMATIC) {
-                            const double vhi = W[Kt], vlo = Kt == 0 ? 0.0 : W[Kt - 1];
-                            double V = vlo + (vhi - vlo) * cs_uniform(a, run, t, 1);
-                            sh.bc[2] = nd * V - floor(nd * V);
-                        }
-                    }
-                    __syncthreads();
-                    const long long Kt = sh.bi[0];
-                    const double V = sh.bc[2];
-                    for (long long i = tid; i < n; i += B) {
-                        if (i == Kt) { anc[i] = kt1; continue; }
-                        double u = mode == SYSTEMATIC ? V + (double)i : cs_uniform(a, run, t, 2 + i) + (double)i;
-                        u /= nd;
-                        anc[i] = (uint32_t)first_above(W, n, u);
-                    }
-                } else {                                              // RESIDUAL :558-642
-                    for (long long i = tid; i < n; i += B) {
-                        const int e = (int)floor(nd * w[i]);
-                        const int card = e > 0 ? e : 0;
-                        Lx[i] = card;
-                        W[i] = w[i] * nd - (double)card / nd;         // residual weight (kept quirk: floor / N)
-                        anc[i] = 0u;
-                    }
-                    __syncthreads();
-                    const long long l = cta_scan(Lx, n, sh.scan_i);   // inclusive: deterministic offspring of parents 0..i
-                    const long long dk_hi = Lx[kt1], dk_lo = kt1 > 0 ? Lx[kt1 - 1] : 0;
-                    const double rk = W[kt1];
-                    const double prob1 = 1.0 / (nd * w[kt1]);
-                    const double prob2 = rk / (nd * w[kt1] * (double)(n - l));
-                    for (long long j = tid; j < n; j += B) {
-                        double p = (j >= dk_lo && j < dk_hi) ? prob1 : 0.0;
-                        if (l < n ? j >= l : j == n - 1) p = prob2;
-                        P[j] = p;
-                        // deterministic offspring: slot j < l belongs to the first parent whose running count exceeds j
-                        if (j < l) {
-                            long long lo2 = 0, hi2 = n - 1;
-                            while (lo2 < hi2) { long long mid = (lo2 + hi2) >> 1; if ((long long)Lx[mid] > j) hi2 = mid; else lo2 = mid + 1; }
-                            anc[j] = (uint32_t)lo2;
-                        }
-                    }
-                    __syncthreads();
-                    const double ptot = cta_scan(P, n, sh.scan_d);
-                    const double rtot = cta_scan(W, n, sh.scan_d);    // running sums of the residual weights
-                    if (tid == 0) {
-                        const long long Kt = sample_cdf(P, n, ptot, cs_uniform(a, run, t, 0));
-                        sh.bi[0] = Kt;
-                        if (wr < T) refidx[wr] = (uint32_t)Kt;        // :627
-                        if (dk_hi == dk_lo) anc[Kt] = kt1;            // :629-633 (the "not in D" branch never fires)
-                    }
-                    __syncthreads();
-                    const long long Kt = sh.bi[0];
-                    if (l < n)
-                        for (long long k = l + tid; k < n; k += B)
-                            if (k != Kt) anc[k] = (uint32_t)sample_cdf(W, n, rtot, cs_uniform(a, run, t, 2 + k));
-                }
-                __syncthreads();
-            }
-            // ---- AL history row (post-resampling values, ancestors, normalised log-weights)
-            if (a.anc_out || a.val_out || a.lw_out) {
-                const size_t row = ((size_t)run * (size_t)T + (size_t)t) * (size_t)n;
-                for (long long i = tid; i < n; i += B) {
-                    const uint32_t p = resampled ? anc[i] : (uint32_t)i;
-                    if (a.anc_out) a.anc_out[row + i] = p;
-                    if (a.val_out) a.val_out[row + i] = x[p];
-                    if (a.lw_out) a.lw_out[row + i] = resampled ? -log_n : lw[i] - lse;
-                }
-            }
-            if (a.res_out && tid == 0) a.res_out[run * T + t] = resampled;
-            __syncthreads();
-        }
-        if (tid == 0) a.lognc[run] = path;
-        for (long long t = tid; t < T; t += B) a.refidx_out[run * T + t] = refidx[t];
-        __syncthreads();
-    }
-}
 
 // sampler::GetALineInd(n) for every n and GetALineSpace (sampler.h:445-476): one thread walks one particle's line backwards.
 __global__ void __launch_bounds__(256) k_ancestor_lines(const uint32_t* anc, const double* values, long long T, long long n, uint32_t* lines,
@@ -314,7 +72,8 @@ void run_chains(const double* y_host, long T, long particles, double phi, double
     if (val_out) d_val = DevBuf(sizeof(double) * hist);
     if (lw_out) d_lw = DevBuf(sizeof(double) * hist);
     if (res_out) d_res = DevBuf(sizeof(int) * runs * T);
-    CsmcArgs a{};
+    CsmcArgs<LGSS> a{};
+    a.thr = 0.5 * (double)n; a.run0 = 0; a.keep_refidx = 0; a.t_cap = T;   // SetResampleParams(mode, 0.5), a fresh sampler object per chain
     a.mp = lgss_params(y.as<double>(), phi, var_evol, x0, var_obs);
     a.T = T; a.n = n; a.n_chains = n_chains; a.runs_per_chain = runs_per_chain;
     a.modes = modes.as<int>(); a.ref = ref.as<double>(); a.seed = seed; a.zin = zin.as<double>(); a.uin = uin.as<double>();
@@ -327,7 +86,7 @@ void run_chains(const double* y_host, long T, long particles, double phi, double
     // compareNCestimates, which use the legacy stream) overlaps with them instead of queueing behind one long kernel.
     cudaStream_t cs = nullptr;
     SMCB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    k_csmc_chain<<<(unsigned)n_chains, CS_THREADS, 0, cs>>>(a);
+    k_csmc_chain<LGSS><<<(unsigned)n_chains, CS_THREADS, 0, cs>>>(a);
     cudaError_t le = cudaGetLastError();
     try {
         if (le == cudaSuccess && overlap) overlap();

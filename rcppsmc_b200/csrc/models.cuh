@@ -174,6 +174,8 @@ struct LGSS {
         x[0] = p.phi * x[0] + (0.0 + p.sd_evol * z[0]);
         lw += loglik(p, p.y[t], x[0]);
     }
+    // pfWeight of the conditional move (src/cSMCexamples.cpp:203-210): the reference particle's value has just been pinned
+    __device__ static __forceinline__ void weight(long long t, const double (&x)[D], double& lw, const Params& p) { lw += loglik(p, p.y[t], x[0]); }
     __device__ static __forceinline__ void shift_stat(const double (&x)[D], double (&h)[1]) { h[0] = 0.0; }
     __device__ static __forceinline__ void observe(const double (&x)[D], const double* shift, double (&f)[1]) { f[0] = 0.0; }
     __device__ static __forceinline__ void finish_obs(const double* v, const double* shift, double* out) {}
