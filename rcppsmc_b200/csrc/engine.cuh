@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
     __shared__ double s_lw[2][Q][ASYNC ? STEP_THREADS : 1];     // stored log-weights (no resampling last step), likewise
     __shared__ unsigned char* s_isl_base[ISLAND ? ISL_MAX : 1];  // island mode: every rank's slab (table for the cold decode paths)
     __shared__ uint32_t s_zoff[ISLAND ? ISL_MAX + 1 : 1], s_eoff[ISLAND ? ISL_MAX + 1 : 1];   // zero slots / surplus entries before each rank
+    __shared__ uint32_t s_hot[3];   // island mode: groups [s_hot[0], s_hot[1]) need no cold path; s_hot[2] = helper blocks for the rest
+    uint32_t vp0 = p0, vstride = stride;   // which groups this thread takes in a sweep: g = vp0 (mod vstride)
     if (ISLAND) {
         if (tid < ISL_MAX) s_isl_base[tid] = a.isl.base[tid];
         __syncthreads();
@@ -258,15 +260,75 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             __threadfence_system();
         }
         __syncthreads();
+        // Hot range of bitmap words: every zero-count slot in it has its surplus entry in this rank's OWN list, i.e. its local
+        // rank r satisfies 0 <= r + zrel and r + zrel < elen.  zbase (rank of a word's first slot) is monotone: two 32-ary
+        // searches by two warps (the array was just written by the map pass: L2 hits).
+        if (warp < 2) {
+            const long long zr = (long long)s_zoff[a.isl.rank] - (long long)s_eoff[a.isl.rank];
+            const long long elen = (long long)s_eoff[a.isl.rank + 1] - (long long)s_eoff[a.isl.rank];
+            const uint32_t nw = (n32 + 31u) >> 5;
+            const long long key = warp == 0 ? -zr : elen - zr + 1;     // first word whose rank base is >= key
+            uint32_t lo = 0u, hi = nw;
+            if (key > 0) {
+                while (hi > lo) {
+                    const uint32_t len = hi - lo, st = (len + 31u) >> 5;
+                    const uint32_t idx = lo + (uint32_t)lane * st;
+                    const bool valid = idx < hi;
+                    const bool pred = valid && (long long)__ldcg(a.am.zbase + (valid ? idx : lo)) >= key;
+                    const unsigned m = __ballot_sync(SMCB_FULL, pred);
+                    if (m == 0u) { lo = lo + ((len - 1u) / st) * st + 1u; }
+                    else {
+                        const uint32_t f = (uint32_t)__ffs(m) - 1u;
+                        if (f == 0u) { hi = lo; break; }
+                        hi = lo + f * st;
+                        lo = lo + (f - 1u) * st + 1u;
+                    }
+                }
+            } else hi = 0u;                                           // every word qualifies
+            if (lane == 0) {
+                constexpr uint32_t GPW = 32u / (uint32_t)Q;             // groups per bitmap word
+                if (warp == 0) s_hot[0] = min(hi * GPW, ngroups);
+                else {
+                    uint32_t wh = hi > 0u ? hi - 1u : 0u;                // words below this one are hot; the last word never is
+                    if (wh > nw - 1u) wh = nw - 1u;
+                    s_hot[1] = min(wh * GPW, ngroups);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_hot[1] < s_hot[0]) s_hot[1] = s_hot[0];
+            // helper blocks for the boundary groups.  A helper iteration waits for NVLink round trips, so a helper thread gets at
+            // most a quarter of the iterations a thread of the middle runs (the helpers must not outlast the middle); if that
+            // takes more than an eighth of the grid, everybody runs the island-capable loop instead.
+            const uint32_t boundary = s_hot[0] + (ngroups - s_hot[1]);
+            const uint32_t iters_mid = ngroups / (gridDim.x * STEP_THREADS) + 1u;
+            const uint32_t per_thread = iters_mid >= 8u ? iters_mid / 4u : 1u;
+            uint32_t h = (boundary + STEP_THREADS * per_thread - 1u) / (STEP_THREADS * per_thread);
+            if (8u * h > gridDim.x || (a.dbg & 256)) h = 0xffffffffu;
+            s_hot[2] = h;
+        }
+        __syncthreads();
     }
     const uint32_t zoff_mine = (ISLAND && decode) ? s_zoff[a.isl.rank] : 0u;
     const uint32_t zrel = (ISLAND && decode) ? zoff_mine - s_eoff[a.isl.rank] : 0u;   // local zero-slot rank -> position in the own surplus list
     const uint32_t elen_mine = (ISLAND && decode) ? s_eoff[a.isl.rank + 1] - s_eoff[a.isl.rank] : 0u;
     const uint32_t* const own_list = a.am.surplus + (int32_t)zrel;   // indexed by the local zero-slot rank
+    // One sweep over the groups g of [g_begin, g_end) with g = vp0 (mod vstride), with its own pipeline prologue; the look-ahead is
+    // clamped to the range.  HOT = every group of the range finds its surplus entries in this rank's own list: the single-GPU
+    // decode.  Without islands there is one such sweep over everything.  In island mode the groups near the island boundaries
+    // -- found once per kernel by a search over the rank bases -- are handed to a few HELPER blocks that run the island-capable
+    // version on them while all other blocks run the single-GPU loop over the middle (which then carries neither the range check
+    // nor the cold paths: these cost the loop the constants it otherwise keeps in uniform registers, +13 % instructions).
+    auto sweep = [&](auto hot_tag, uint32_t g_begin, uint32_t g_end) {
+    constexpr bool HOT = decltype(hot_tag)::value;
+    if (g_begin >= g_end) return;
     // The look-ahead of the last iterations runs past the end of the population; it is clamped to the last group instead of
     // being branched around (the redundant copies are harmless), so that the loop body stays one basic block in which the
     // compiler can interleave the arithmetic of the thread's Q particles.
-    const uint32_t glast = ngroups - 1u;
+    const uint32_t glast = g_end - 1u;
+    const uint32_t p0s = vp0 >= g_begin ? vp0 : vp0 + ((g_begin - vp0 + vstride - 1u) / vstride) * vstride;   // this thread's first group of the range
+    if (p0s >= g_end) return;
     auto mask_word = [&](uint32_t p) { return (min(p, glast) * Q) >> 5; };
     auto stageA = [&](uint32_t p, unsigned par) {
         if (ASYNC && decode) {
@@ -288,7 +350,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         const uint32_t bit = s0 & 31u;
         const uint32_t rank = bA + __popc(mA & ((1u << bit) - 1u));
         const uint32_t zq = (mA >> bit) & ((1u << Q) - 1u);      // the group's zero-count flags
-        if (ISLAND) {
+        if (ISLAND && !HOT) {
             const uint32_t lo = rank + zrel;                      // wraps to a huge value in front of the own list
             if (!(lo <= elen_mine && lo + (uint32_t)__popc(zq) <= elen_mine)) return cold(zq, zoff_mine + rank);
         }
@@ -324,7 +386,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         if (ASYNC) {
             const uint32_t s0 = Q * min(p, glast);
             const unsigned bx = sa_x + buf * XBUF, bl = sa_lw + buf * LBUF;
-            if (ISLAND && (zf >> 16)) {   // cold: some parent of this group is copied from its owner's slab over NVLink
+            if (ISLAND && !HOT && (zf >> 16)) {   // cold: some parent of this group is copied from its owner's slab over NVLink
 #pragma unroll 1
                 for (int h = 0; h < Q; ++h) {
                     const int owner = ((zf >> (16 + h)) & 1u) ? (int)((zf >> (20 + 3 * h)) & 7u) : a.isl.rank;
@@ -344,7 +406,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             }
         }
     };
-    // Pipeline: iteration i (parity par = i & 1) works on group G_i = p0 + i S and issues, in this order,
+    // Pipeline: iteration i (parity par = i & 1) works on group G_i = p0s + i S and issues, in this order,
     //   group "AB":  stage B for G_{i+4} (rank -> surplus entries, from the words stage A fetched in iteration i-2),
     //                stage A for G_{i+6} (bitmap word + rank base)
     //   group "C":   the parents' state for G_{i+2} (ancestors from the entries stage B fetched in iteration i-2), into the
@@ -359,7 +421,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         if (decode) {
             uint32_t mA[6], bA[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { const uint32_t w = mask_word(p0 + (uint32_t)k * stride); mA[k] = __ldg(a.am.zmask + w); bA[k] = __ldg(a.am.zbase + w); }
+            for (int k = 0; k < 6; ++k) { const uint32_t w = mask_word(p0s + (uint32_t)k * vstride); mA[k] = __ldg(a.am.zmask + w); bA[k] = __ldg(a.am.zbase + w); }
             s_mk[0][0][tid] = mA[4]; s_mk[0][1][tid] = bA[4];
             s_mk[1][0][tid] = mA[5]; s_mk[1][1][tid] = bA[5];
             uint32_t e0[Q], e1[Q];
@@ -383,19 +445,19 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             auto cold_smem = [&](unsigned base) {
                 return [&, base](uint32_t zq, uint32_t m0) { return isl_cold_group(zq, m0, base, s_eoff, s_isl_base, a.isl.off_surplus, a.isl.world, a.isl.rank); };
             };
-            zf0 = decodeB(p0, mA[0], bA[0], [&](int h, const uint32_t* g) { e0[h] = *g; }, cold_reg(e0));
-            zf1 = decodeB(p0 + stride, mA[1], bA[1], [&](int h, const uint32_t* g) { e1[h] = *g; }, cold_reg(e1));
-            zf_old = decodeB(p0 + 2 * stride, mA[2], bA[2], [&](int h, const uint32_t* g) { cp_async4(sa_sp + (unsigned)h * ST4, g); }, cold_smem(sa_sp));
-            zf_new = decodeB(p0 + 3 * stride, mA[3], bA[3], [&](int h, const uint32_t* g) { cp_async4(sa_sp + SPBUF + (unsigned)h * ST4, g); }, cold_smem(sa_sp + SPBUF));
-            const uint32_t self0 = Q * min(p0, glast), self1 = Q * min(p0 + stride, glast);
+            zf0 = decodeB(p0s, mA[0], bA[0], [&](int h, const uint32_t* g) { e0[h] = *g; }, cold_reg(e0));
+            zf1 = decodeB(p0s + vstride, mA[1], bA[1], [&](int h, const uint32_t* g) { e1[h] = *g; }, cold_reg(e1));
+            zf_old = decodeB(p0s + 2 * vstride, mA[2], bA[2], [&](int h, const uint32_t* g) { cp_async4(sa_sp + (unsigned)h * ST4, g); }, cold_smem(sa_sp));
+            zf_new = decodeB(p0s + 3 * vstride, mA[3], bA[3], [&](int h, const uint32_t* g) { cp_async4(sa_sp + SPBUF + (unsigned)h * ST4, g); }, cold_smem(sa_sp + SPBUF));
+            const uint32_t self0 = Q * min(p0s, glast), self1 = Q * min(p0s + vstride, glast);
 #pragma unroll
             for (int h = 0; h < Q; ++h) { anc0[h] = resolve(zf0, h, e0[h], self0); anc1[h] = resolve(zf1, h, e1[h], self1); }
         } else {
-            readC(anc0, 0u, p0, 0u);
-            readC(anc1, 0u, p0 + stride, 0u);
+            readC(anc0, 0u, p0s, 0u);
+            readC(anc1, 0u, p0s + vstride, 0u);
         }
-        issueC(anc0, zf0, p0, 0u); cp_async_commit();       // together with the surplus entries of G_2 / G_3
-        issueC(anc1, zf1, p0 + stride, 1u); cp_async_commit();
+        issueC(anc0, zf0, p0s, 0u); cp_async_commit();       // together with the surplus entries of G_2 / G_3
+        issueC(anc1, zf1, p0s + vstride, 1u); cp_async_commit();
         cp_async_commit();                                   // empty group: iteration 0 waits for all but the two youngest
     }
     unsigned buf = 0u;
@@ -419,11 +481,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
             // advance the pipeline before the arithmetic of this group
             if (ASYNC) {
                 uint32_t anc[Q];
-                readC(anc, zf_old, p + 2 * stride, buf);
-                const uint32_t zf_cur = stageB(p + 4 * stride, buf);
-                stageA(p + 6 * stride, buf);
+                readC(anc, zf_old, p + 2 * vstride, buf);
+                const uint32_t zf_cur = stageB(p + 4 * vstride, buf);
+                stageA(p + 6 * vstride, buf);
                 cp_async_commit();
-                issueC(anc, zf_old, p + 2 * stride, buf);
+                issueC(anc, zf_old, p + 2 * vstride, buf);
                 cp_async_commit();
                 zf_old = zf_new; zf_new = zf_cur;
                 buf ^= 1u;
@@ -514,9 +576,26 @@ __global__ void __launch_bounds__(STEP_THREADS, SMCB_STEP_MINB) k_step(StepArgs<
         }
     };
     const uint32_t nfull = n32 / Q;                 // groups in which every slot exists
-    for (uint32_t p = p0; p < ngroups; p += stride) {
+    for (uint32_t p = p0s; p < g_end; p += vstride) {
         if (p < nfull) body(std::true_type{}, p);
         else body(std::false_type{}, p);
+    }
+    if (ASYNC) cp_async_wait_all();   // look-ahead copies beyond the range must have landed before the slots are reused
+    };
+    if constexpr (ISLAND && decode) {
+        const uint32_t gA = s_hot[0], gB = s_hot[1], helpers = s_hot[2];
+        if (helpers == 0xffffffffu) {                        // boundaries too large to hand to helpers: everybody, island-capable loop
+            sweep(std::false_type{}, 0u, ngroups);
+        } else if (blockIdx.x + helpers >= gridDim.x) {      // a helper block: boundary groups only
+            vp0 = (blockIdx.x - (gridDim.x - helpers)) * STEP_THREADS + tid; vstride = helpers * STEP_THREADS;
+            sweep(std::false_type{}, 0u, gA);
+            sweep(std::false_type{}, gB, ngroups);
+        } else {                                             // the middle, shared by all other blocks
+            vstride = (gridDim.x - helpers) * STEP_THREADS;
+            sweep(std::true_type{}, gA, gB);
+        }
+    } else {
+        sweep(std::true_type{}, 0u, ngroups);
     }
     };
     if (PHASE != PHASE_INIT && resampled) run(std::true_type{});
