@@ -75,12 +75,20 @@ inline LinRegLA_result LinRegLA_impl(const vec& Data_nx2, const vec& intemps, un
 }
 inline LinRegLA_result LinRegLA_adapt_impl(const vec& Data_nx2, unsigned long lNumber, double resampTol, double tempTol, uint64_t seed = 1,
                                            long max_temps = 512) {
-    const long N = (long)lNumber, C = max_temps;
-    LinRegLA_result r{0, vec(3 * N * C), vec(N * C), vec(N * C), vec(N * C), vec(C), vec(C), vec(C), 0, 0, 0, 0};
+    // The history is sized by the temperature capacity (6 doubles per particle and temperature, on the device and here), while
+    // a run typically needs 20-40 temperatures: a small capacity first, the caller's only if the schedule turns out longer (the
+    // draws are counter-based, so the repeat reproduces the same run).
+    const long N = (long)lNumber;
+    LinRegLA_result r{};
     double nc[4];
-    const long L = smcb200_LinRegLA_adapt(Data_nx2.data(), (long)Data_nx2.size() / 2, N, resampTol, tempTol, seed, nullptr, 0, nullptr, 0, C,
-                                          r.theta.data(), r.loglike.data(), r.logprior.data(), r.Weights.data(), r.ESS.data(), r.Temps.data(),
-                                          r.mcmcRepeats.data(), nc, nullptr);
+    long L = 0;
+    for (long C : {max_temps > 64 ? 64L : max_temps, max_temps}) {
+        r = LinRegLA_result{0, vec(3 * N * C), vec(N * C), vec(N * C), vec(N * C), vec(C), vec(C), vec(C), 0, 0, 0, 0};
+        L = smcb200_LinRegLA_adapt(Data_nx2.data(), (long)Data_nx2.size() / 2, N, resampTol, tempTol, seed, nullptr, 0, nullptr, 0, C,
+                                   r.theta.data(), r.loglike.data(), r.logprior.data(), r.Weights.data(), r.ESS.data(), r.Temps.data(),
+                                   r.mcmcRepeats.data(), nc, nullptr);
+        if (L > 0 || C == max_temps || std::string(smcb200_last_error()).find("more temperatures than max_temps") == std::string::npos) break;
+    }
     if (L <= 0) throw error((int)-L, smcb200_last_error());
     r.L = L;
     r.theta.resize(3 * N * L); r.loglike.resize(N * L); r.logprior.resize(N * L); r.Weights.resize(N * L);

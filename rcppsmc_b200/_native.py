@@ -242,13 +242,19 @@ def LinRegLA_adapt(Data, lNumber, resampTol=0.5, tempTol=0.9, seed=1, noise=None
     log-evidence estimates."""
     flat, n_obs = _la_data(Data)
     N = int(lNumber)
-    th = np.empty(max_temps * 3 * N); ll = np.empty(max_temps * N); lp = np.empty(max_temps * N); w = np.empty(max_temps * N)
-    ess, temps, reps, acc = (np.empty(max_temps) for _ in range(4))
-    nc = np.empty(4)
     z, u = _f64(noise), _f64(uniforms)
-    L = lib().smcb200_LinRegLA_adapt(_dp(flat), n_obs, N, resampTol, tempTol, seed, _dp(z), 0 if z is None else z.size, _dp(u),
-                                     0 if u is None else u.size, max_temps, _dp(th), _dp(ll), _dp(lp), _dp(w), _dp(ess), _dp(temps),
-                                     _dp(reps), _dp(nc), _dp(acc))
+    # The history (6 doubles per particle and temperature, on the device and here) is sized by the temperature capacity, while a
+    # run typically needs 20-40 temperatures: try a small capacity first and repeat with the caller's only if the schedule turns
+    # out longer (the draws are counter-based, so the repeat reproduces the same run).
+    for cap in ([64, max_temps] if max_temps > 64 else [max_temps]):
+        th = np.empty(cap * 3 * N); ll = np.empty(cap * N); lp = np.empty(cap * N); w = np.empty(cap * N)
+        ess, temps, reps, acc = (np.empty(cap) for _ in range(4))
+        nc = np.empty(4)
+        L = lib().smcb200_LinRegLA_adapt(_dp(flat), n_obs, N, resampTol, tempTol, seed, _dp(z), 0 if z is None else z.size, _dp(u),
+                                         0 if u is None else u.size, cap, _dp(th), _dp(ll), _dp(lp), _dp(w), _dp(ess), _dp(temps),
+                                         _dp(reps), _dp(nc), _dp(acc))
+        if L > 0 or cap == max_temps or b"more temperatures than max_temps" not in lib().smcb200_last_error():
+            break
     if L <= 0:
         raise SmcError(f"smcb200 status {-L}: {lib().smcb200_last_error().decode()}")
     return {"theta": th[:L * 3 * N].reshape(L, 3, N).transpose(2, 1, 0), "loglike": ll[:L * N].reshape(L, N).T,

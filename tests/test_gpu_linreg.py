@@ -91,3 +91,12 @@ def test_data_annealing_known_log_evidence(smc):
     out = smc.LinReg(data, 1 << 17, seed=4)
     assert abs(out["logNC"] - (-309.9)) < 0.25       # man/LinReg.Rd:78-80
     assert abs(out["weights"].sum() - 1.0) < 1e-9
+
+
+def test_adaptive_schedule_longer_than_the_first_history_capacity(smc):
+    """the wrappers size the history for 64 temperatures first and repeat with the caller's capacity when the schedule is longer"""
+    Data = H.radiata()[:, :2]
+    r = smc.LinRegLA_adapt(Data, 600, 0.5, 0.997, seed=3)
+    L = r["Temps"].size
+    assert L > 64 and r["Temps"][-1] == 1.0 and np.all(np.diff(r["Temps"]) > 0)
+    assert r["theta"].shape == (600, 3, L) and np.isfinite(r["logNC_standard"])
