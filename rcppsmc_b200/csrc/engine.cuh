@@ -1,12 +1,15 @@
 // Device SMC engine: the reference's smc::sampler loop (inst/include/sampler.h:481-550 Initialise,
-// :701-764 IterateEss) re-designed as two kernels per time step that never return to the host:
+// :701-764 IterateEss) re-designed as four kernels per time step, chained by programmatic dependent launch, that never return
+// to the host:
 //
-//   k_step   gather(ancestor) + pfMove/pfInitialise functor + log-weight + online (m, s, q, g) partials
+//   k_step   gather(ancestor) + pfMove/pfInitialise functor + log-weight + shifted weight exp(lw - c) + partial sums
 //            + fused weighted moments of the PREVIOUS population; the last block to finish merges the
 //            partials and writes the step scalars (logNC increment, path, ESS, resample decision, the
 //            resampling uniform) into the device control block  -> moveset.h:133-168, sampler.h:495-511,
 //            :707-723, :559-571
-//   k_resample_scan (resample.cuh)   weights -> ancestor map, skipped on device when ESS >= threshold
+//   k_rs_mass / k_rs_count / k_rs_map (resample.cuh)   weights -> ancestor map as three streaming passes, skipped on the
+//            device when ESS >= threshold (k_resample_scan: the single-pass look-back kernel of round 1, kept for A/B runs)
+//   small.cuh   populations up to 2^16: the whole filter as ONE cooperative launch (Sampler::RunFilterSmall)
 //
 // Population layout: structure-of-arrays, D double arrays of length N, double-buffered (the gather is
 // out-of-place), one log-weight array; the reference's AoS std::vector<Space> + arma::vec

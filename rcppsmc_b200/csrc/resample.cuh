@@ -1,16 +1,20 @@
-// Device resampling: weights -> children counts -> the reference's in-place ancestor map, in ONE pass.
+// Device resampling: weights -> children counts -> the reference's in-place ancestor map.
 //
 // Replaces sampler::Resample (reference inst/include/sampler.h:779-868):
-//   * cumulative sum (arma::cumsum, :811/:833)      -> single-pass decoupled look-back scan of the
-//     normalised weights quantised to the 2^-52 grid (u64 integer scan: exact, order-independent)
+//   * cumulative sum (arma::cumsum, :811/:833)      -> exact scan of the normalised weights quantised to the 2^-52 grid
+//     (sums of such values below 2 are exact in fp64 in any order, so a parallel scan equals the sequential one bit for bit)
 //   * two-pointer count loops (:805-843)             -> closed form per parent k:
 //         c(k) = #{ j < N : fl(j/N) < fl(W[k] - u_j) },   count[k] = c(k) - c(k-1)
 //     evaluated with the reference's own floating-point predicate
-//   * count -> index map (:846-857)                  -> second chained look-back scan (zero-count slots)
-//     Z[s] = #{s' < s : count[s'] = 0};  E[k] = c(k-1) - k + Z[k] = surplus children of parents < k;
+//   * count -> index map (:846-857)                  -> Z[s] = #{s' < s : count[s'] = 0};
+//     E[k] = c(k-1) - k + Z[k] = surplus children of parents < k;
 //     parent k writes itself to surplus[E[k] .. E[k]+count[k]-2]; a zero-count slot s takes surplus[Z[s]].
 //   * replication (:860-864)                         -> NOT done here: the ancestor of slot s is decoded in
 //     the next propagate kernel's gather from (zmask, zbase, surplus): 2 bits + 4 B per zero-count slot.
+// Two implementations of the SYSTEMATIC / STRATIFIED path: three streaming passes without inter-block waiting (k_rs_mass,
+// k_rs_count, k_rs_map: the production path, second half of this file) and ONE pass with decoupled look-back scans
+// (k_resample_scan: round 1, kept for A/B measurements and as the injected-counts surface k_count_map).  MULTINOMIAL / RESIDUAL:
+// the engine's native definitions (integer scan, iid draws through the exact integer inverse CDF, counts -> map).
 #pragma once
 #include <functional>
 
