@@ -261,6 +261,14 @@ __device__ __forceinline__ int children_upto(double W, const ScanArgs& a, long l
         double fl = floor(g);
         long long js = (long long)fmin(fl, nd);
         double fr = g - fl;
+        if (fr >= 9.5367431640625e-07 && fr <= 1.0 - 9.5367431640625e-07 && js >= 1 && js <= nthr - 2) {
+            // the usual case, straight-line: the loop below would find child js-1 surely below W, child js+1 surely above, and
+            // evaluate the reference's predicate for child js alone (same expression, same bits)
+            const double U = a.ustrat ? a.ustrat[step * (nthr + 1) + js]
+                                      : u64_to_unit(philox_draw(a.seed_ptr ? *a.seed_ptr : a.seed, STREAM_RESAMPLE, (uint32_t)step, (uint64_t)js, 0).a);
+            const double uj = 0.0 + (inv_n - 0.0) * U;
+            return (int)js + (((W - uj) > ((double)js / nd)) ? 1 : 0);
+        }
         long long lo = js - 1 < 0 ? 0 : js - 1;
         long long hi = js + 1 > nthr - 1 ? nthr - 1 : js + 1;
         long long c = lo;
