@@ -183,11 +183,26 @@ void run_blockpf(const double* y_host, long T, long particles, long lag, uint64_
     SMCB_CUDA(cudaMemcpy(d_y.p, y_host, sizeof(double) * T, cudaMemcpyHostToDevice));
     SMCB_CUDA(cudaMemcpy(d_sig.p, sig.data(), sizeof(double) * (L + 1), cudaMemcpyHostToDevice));
     SMCB_CUDA(cudaMemcpy(d_sigh.p, sigh.data(), sizeof(double) * (L + 1), cudaMemcpyHostToDevice));
-    DevBuf live(sizeof(double) * 2 * (size_t)L * n), frozen(sizeof(double) * (size_t)T * n), lw(sizeof(double) * n);
-    DevBuf anc(sizeof(uint32_t) * (size_t)T * n), resflag(sizeof(int) * T), ess_tr(sizeof(double) * T), ctrl(sizeof(BpfCtrl));
+    // The large buffers (the frozen rows and ancestor rows are T x N) are kept per calling thread and reused while the shape
+    // matches: allocating and freeing 1.3 GB per call cost as much as the filter itself at 2^20 paths x 100 steps.
+    struct Workspace {
+        long T = -1; long long n = -1; int L = -1;
+        DevBuf live, frozen, lw, anc, resflag, ess_tr, ctrl, zmask, zbase, surplus, status, cslot;
+    };
+    thread_local Workspace ws;
     const long long ntiles = scan_tiles(n);
-    DevBuf zmask(sizeof(uint32_t) * ((n + 31) / 32 + 64)), zbase(sizeof(uint32_t) * ((n + 31) / 32 + 64)), surplus(sizeof(uint32_t) * n);
-    DevBuf status(sizeof(unsigned long long) * 3 * ntiles);
+    if (ws.T != T || ws.n != n || ws.L != L) {
+        ws = Workspace{};
+        ws.live = DevBuf(sizeof(double) * 2 * (size_t)L * n); ws.frozen = DevBuf(sizeof(double) * (size_t)T * n); ws.lw = DevBuf(sizeof(double) * n);
+        ws.anc = DevBuf(sizeof(uint32_t) * (size_t)T * n); ws.resflag = DevBuf(sizeof(int) * T); ws.ess_tr = DevBuf(sizeof(double) * T);
+        ws.ctrl = DevBuf(sizeof(BpfCtrl));
+        ws.zmask = DevBuf(sizeof(uint32_t) * ((n + 31) / 32 + 64)); ws.zbase = DevBuf(sizeof(uint32_t) * ((n + 31) / 32 + 64));
+        ws.surplus = DevBuf(sizeof(uint32_t) * n); ws.status = DevBuf(sizeof(unsigned long long) * 3 * ntiles);
+        ws.cslot = DevBuf(sizeof(uint32_t) * resample_cslot_entries(n));
+        ws.T = T; ws.n = n; ws.L = L;
+    }
+    DevBuf &live = ws.live, &frozen = ws.frozen, &lw = ws.lw, &anc = ws.anc, &resflag = ws.resflag, &ess_tr = ws.ess_tr, &ctrl = ws.ctrl;
+    DevBuf &zmask = ws.zmask, &zbase = ws.zbase, &surplus = ws.surplus, &status = ws.status;
     int dev = 0, sms = 0;
     SMCB_CUDA(cudaGetDevice(&dev));
     SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -220,8 +235,7 @@ void run_blockpf(const double* y_host, long T, long particles, long lag, uint64_
     sc.step_ptr = &a.ctrl->T; sc.seed = seed; sc.ticket = &a.ctrl->ticket;
     sc.ws = ScanWs{status.as<unsigned long long>(), status.as<unsigned long long>() + ntiles, status.as<unsigned long long>() + 2 * ntiles};
     sc.am = am; sc.n_glob = n;
-    DevBuf cslot(sizeof(uint32_t) * resample_cslot_entries(n));
-    sc.cslot = cslot.as<uint32_t>();
+    sc.cslot = ws.cslot.as<uint32_t>();
     for (long t = 0; t < T; ++t) {
         if (t == 0) k_bpf_step<true><<<grid, 256, 0, st>>>(a);
         else k_bpf_step<false><<<grid, 256, 0, st>>>(a);
