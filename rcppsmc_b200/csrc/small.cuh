@@ -281,30 +281,28 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
         tick(1);
 
         // ---- phase B: every block closes the step for itself (same order everywhere => same bits everywhere)
-        auto merged = [&](double (&v)[NF]) {   // called by warp 0
-            v[0] = -INFINITY;
-#pragma unroll
-            for (int f = 1; f < NF; ++f) v[f] = 0.0;
-            for (int b = lane; b < nb; b += 32) {
-                v[0] = fmax(v[0], __longlong_as_double((long long)s_out[b][0]));
-#pragma unroll
-                for (int f = 1; f < NF; ++f) v[f] += __longlong_as_double((long long)s_out[b][f]);
-            }
-            v[0] = warp_max(v[0]);
-#pragma unroll
-            for (int f = 1; f < NF; ++f) v[f] = warp_sum(v[f]);
-        };
-        __shared__ double s_fin[SF_NV];
+        // every warp merges some of the NF values over the blocks (value f: lane-strided partial sums, then the shuffle tree --
+        // the same order of additions in every block); the step's resampling uniform is drawn by another thread meanwhile
+        __shared__ double s_fin[SF_NV], s_tmp[SF_NV];
         __shared__ int s_bad;
-        if (warp == 0) {
-            double v[NF];
-            merged(v);
-            if (lane == 0) {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) s_fin[f] = v[f];
-                const double d = v[0] - cs;
-                s_bad = (!observe_only && (d <= -250.0 || d >= 250.0) && v[0] != -INFINITY) ? 1 : 0;
+        auto merged = [&](double* out) {
+            for (int f = warp; f < NF; f += SF_THREADS / 32) {
+                double v = f == 0 ? -INFINITY : 0.0;
+                for (int b = lane; b < nb; b += 32) {
+                    const double x = __longlong_as_double((long long)s_out[b][f]);
+                    v = f == 0 ? fmax(v, x) : v + x;
+                }
+                v = f == 0 ? warp_max(v) : warp_sum(v);
+                if (lane == 0) out[f] = v;
             }
+        };
+        merged(s_fin);
+        if (tid == SF_THREADS - 1 && !observe_only)
+            S.u_res = a.ures ? a.ures[tcur] : u64_to_unit(philox_draw(seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
+        __syncthreads();
+        if (tid == 0) {
+            const double d = s_fin[0] - cs;
+            s_bad = (!observe_only && (d <= -250.0 || d >= 250.0) && s_fin[0] != -INFINITY) ? 1 : 0;
         }
         __syncthreads();
         double cs_used = cs;
@@ -344,14 +342,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
                 for (int f = 0; f < NF; ++f) mine[f] = (unsigned long long)__double_as_longlong(v[f]);
             }
             sf_exchange(a.sync, 1, (int)(step & 1), sync_target, mine, NF, s_out);
-            if (warp == 0) {
-                double v[NF];
-                merged(v);
-                if (lane == 0) {
-                    s_fin[1] = v[1]; s_fin[2] = v[2];
+            merged(s_tmp);
+            __syncthreads();
+            if (tid == 0) {
+                s_fin[1] = s_tmp[1]; s_fin[2] = s_tmp[2];
 #pragma unroll
-                    for (int j = 0; j < G; ++j) s_fin[4 + j] = v[4 + j];
-                }
+                for (int j = 0; j < G; ++j) s_fin[4 + j] = s_tmp[4 + j];
             }
             __syncthreads();
             cs_used = M;
@@ -379,7 +375,6 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_filter_small(SmallArgs<Model>
                 double c_next = base_next + (mx - cbase);
                 if (!(fabs(c_next) < 1e300)) c_next = base_next;
                 S.cbase = base_next; S.cs = c_next;
-                S.u_res = a.ures ? a.ures[tcur] : u64_to_unit(philox_draw(seed, STREAM_RESAMPLE, (uint32_t)tcur, ~0ull, 1).a);
                 if (blockIdx.x == 0 && tcur < a.tcap) { a.tr.lognc[tcur] = path; a.tr.ess[tcur] = ess; a.tr.resampled[tcur] = res; }
             }
         }
